@@ -1,0 +1,172 @@
+"""fa_b200.py — host-side Python mirror of the reference's operator interface, over the C ABI (include/fa_b200.h).
+
+PyTorch is used only for device memory and streams.  Every call goes through libfa_b200.so (hand-written
+sm_100a CUDA); if the library is missing or the device is not a B200 the call raises — there is no fallback.
+
+Mirrors of the reference interface:
+  multi_head_attention(Q, K, V, num_heads)      same signature as the reference's check.py:4 ((batch, seq_len,
+                                                d_model) tensors); runs on the GPU through fa_fwd_strided, so
+                                                check.py's layout needs no transpose.  Returns the output only
+                                                (the fused kernel never materialises `attn`).
+  two_loader_mha_flash_attention(Q,K,V,O,...)   the kernel's argument list (kernels/FlashAttention.cuh:59-63)
+                                                on [B,H,N,d] tensors of any supported dtype.
+  attention_forward(q, k, v, ...)               general entry: GQA, causal, LSE, strides taken from the tensors.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libfa_b200.so")
+SOURCES = [os.path.join(_HERE, "kernels", f) for f in
+           ("FlashAttention.cu", "FlashAttention.cuh", "loaders.cuh", "computers.cuh", "utils.cuh")]
+NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+FA_DTYPE_F32, FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1, 2
+EXPORTS = ["fa_fwd", "fa_fwd_strided", "fa_mha_fwd_f32", "fa_fwd_host", "fa_merge_partial", "fa_cast_out",
+           "fa_device_info", "fa_block_q", "fa_block_kv", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
+
+_lib = None
+
+
+class FaError(RuntimeError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc-compile kernels/FlashAttention.cu for sm_100a into libfa_b200.so (in-tree, so it travels with gpurun)."""
+    newest = max(os.path.getmtime(s) for s in SOURCES + [os.path.join(_ROOT, "include", "fa_b200.h")])
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise FaError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FaError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU or PyTorch fallback for this path)")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ip, fl, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+        L.fa_fwd.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, vp]
+        L.fa_fwd_strided.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, ctypes.POINTER(ll), vp]
+        L.fa_mha_fwd_f32.argtypes = [vp, vp, vp, vp] + [ip] * 4 + [fl, ip, vp]
+        L.fa_fwd_host.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip]
+        L.fa_merge_partial.argtypes = [vp, vp, vp, vp, ll, ip, ip, vp]
+        L.fa_cast_out.argtypes = [vp, vp, ll, ip, vp]
+        L.fa_device_info.argtypes = [ip, vp]
+        for name in ("fa_block_q", "fa_block_kv", "fa_num_cta"):
+            getattr(L, name).argtypes = [ip, ip]
+        for name in EXPORTS:
+            getattr(L, name).restype = ip
+        L.fa_last_error.restype = ctypes.c_char_p
+        L.fa_version.restype = ctypes.c_char_p
+        L.fa_launch_count.restype = ll
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise FaError(f"{what} failed (code {rc}): {lib().fa_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().fa_launch_count())
+
+
+def _dtype_code(t):
+    import torch
+    return {torch.float32: FA_DTYPE_F32, torch.float16: FA_DTYPE_F16, torch.bfloat16: FA_DTYPE_BF16}[t.dtype]
+
+
+def _stream_ptr(t):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def attention_forward(q, k, v, causal=False, scale=None, return_lse=False, out=None):
+    """q [B,Hq,Nq,d], k/v [B,Hkv,Nk,d] CUDA tensors (any strides with a contiguous last dim). Returns O like q."""
+    import torch
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise FaError("attention_forward needs CUDA tensors (no CPU path exists)")
+    B, Hq, Nq, d = q.shape
+    Bk, Hkv, Nk, dk = k.shape
+    if (Bk, dk) != (B, d) or v.shape != k.shape or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise FaError("shape / dtype mismatch between q, k, v")
+    for t in (q, k, v):
+        if t.stride(-1) != 1:
+            raise FaError("last dimension must be contiguous")
+    if out is None:
+        out = torch.empty_like(q, memory_format=torch.contiguous_format) if q.is_contiguous() else torch.empty_like(q)
+    lse = torch.empty((B, Hq, Nq), device=q.device, dtype=torch.float32) if return_lse else None
+    strides = (ctypes.c_longlong * 12)(*(list(q.stride()[:3]) + list(k.stride()[:3]) + list(v.stride()[:3]) + list(out.stride()[:3])))
+    with torch.cuda.device(q.device):
+        rc = lib().fa_fwd_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                  lse.data_ptr() if lse is not None else None,
+                                  B, Hq, Hkv, Nq, Nk, d, _dtype_code(q), float(scale) if scale else 0.0,
+                                  int(bool(causal)), strides, _stream_ptr(q))
+    _check(rc, "fa_fwd_strided")
+    return (out, lse) if return_lse else out
+
+
+def two_loader_mha_flash_attention(Q, K, V, O, batchSize, numHeads, seqLen, scale, is_causal):
+    """The reference kernel's argument list (kernels/FlashAttention.cuh:59-63) on contiguous [B,H,N,d] CUDA tensors."""
+    import torch
+    d = Q.numel() // (batchSize * numHeads * seqLen)
+    with torch.cuda.device(Q.device):
+        rc = lib().fa_fwd(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), None, batchSize, numHeads, numHeads,
+                          seqLen, seqLen, d, _dtype_code(Q), float(scale), int(bool(is_causal)), _stream_ptr(Q))
+    _check(rc, "fa_fwd")
+    return O
+
+
+def multi_head_attention(Q, K, V, num_heads, causal=False):
+    """check.py:4 signature on CUDA tensors: Q, K, V (batch, seq_len, d_model) -> output (batch, seq_len, d_model)."""
+    bsz, n, d_model = Q.shape
+    dk = d_model // num_heads
+
+    def heads(x):   # a strided view, no copy: [B, N, H, dk] -> [B, H, N, dk]
+        return x.view(bsz, n, num_heads, dk).permute(0, 2, 1, 3)
+
+    import torch
+    out = torch.empty_like(Q)
+    attention_forward(heads(Q), heads(K), heads(V), causal=causal, out=heads(out))
+    return out
+
+
+def attention_forward_host(q, k, v, out, causal=False, scale=None):
+    """End-to-end on HOST tensors (pinned for full PCIe speed): H2D, kernel, D2H inside the C library."""
+    B, Hq, Nq, d = q.shape
+    _, Hkv, Nk, _ = k.shape
+    rc = lib().fa_fwd_host(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), None, B, Hq, Hkv, Nq, Nk, d,
+                           _dtype_code(q), float(scale) if scale else 0.0, int(bool(causal)))
+    _check(rc, "fa_fwd_host")
+    return out
+
+
+def merge_partial(acc_o, acc_lse, part_o, part_lse):
+    """Ring-KV carry: fold a 16-bit partial (O, LSE) over a disjoint key range into the fp32 accumulator, in place."""
+    import torch
+    rows = acc_lse.numel()
+    d = acc_o.shape[-1]
+    with torch.cuda.device(acc_o.device):
+        rc = lib().fa_merge_partial(acc_o.data_ptr(), acc_lse.data_ptr(), part_o.data_ptr(), part_lse.data_ptr(),
+                                    rows, d, _dtype_code(part_o), _stream_ptr(acc_o))
+    _check(rc, "fa_merge_partial")
+
+
+def cast_out(src_f32, dst16):
+    with __import__("torch").cuda.device(src_f32.device):
+        rc = lib().fa_cast_out(src_f32.data_ptr(), dst16.data_ptr(), src_f32.numel(), _dtype_code(dst16), _stream_ptr(src_f32))
+    _check(rc, "fa_cast_out")
+    return dst16

@@ -1,0 +1,368 @@
+// FlashAttention.cu — the launcher: C-ABI implementation of include/fa_b200.h.
+//
+// The reference's kernels/FlashAttention.cu is a translation unit that only includes the header
+// (reference: kernels/FlashAttention.cu:1, everything else commented out) and leaves grid/block/smem
+// to the caller (reference: tests/main.cu:51-61).  Here the launcher owns argument validation, TMA
+// descriptor construction, dynamic shared-memory opt-in, grid shape and kernel dispatch.
+// There is no CPU fallback: on a device that is not sm_100 every entry point fails with FA_ERR_NOT_B200.
+#include "FlashAttention.cuh"
+#include "../../include/fa_b200.h"
+
+#include <cuda_fp16.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define FA_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(FA_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---- device checks -------------------------------------------------------------------------------
+int check_device() {
+    int dev = 0;
+    FA_CUDA(cudaGetDevice(&dev));
+    static std::mutex mu;
+    static int cached[64];   // 0 unknown, 1 ok, -1 not sm_100
+    if (dev < 0 || dev >= 64) return fail(FA_ERR_INVALID_ARGUMENT, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (cached[dev] == 0) {
+        int major = 0;
+        FA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        cached[dev] = (major == 10) ? 1 : -1;
+    }
+    if (cached[dev] < 0)
+        return fail(FA_ERR_NOT_B200, "device %d is not compute capability 10.x; this library has no other path", dev);
+    return FA_OK;
+}
+
+// ---- TMA descriptors -------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// [B, H, N, d] tensor with element strides (sb, sh, sn, 1); box = 64 columns x 128 rows, 128B swizzle.
+int make_tile_map(CUtensorMap* m, const void* base, int dtype, int B, int H, int N, int d, long long sb, long long sh,
+                  long long sn) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const CUtensorMapDataType dt = dtype == FA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)sn * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+    // A size-1 dimension's stride is never used for addressing but must still be a legal value.
+    if (H == 1) strides[1] = strides[0] * (cuuint64_t)N;
+    if (B == 1) strides[2] = strides[1] * (cuuint64_t)H;
+    cuuint32_t box[4] = {(cuuint32_t)fa::kHalfCols, (cuuint32_t)fa::kBlockN, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return FA_OK;
+}
+
+// ---- tcgen05 path ----------------------------------------------------------------------------------
+template <int D, int STAGES, int DT>
+int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p,
+                 cudaStream_t st) {
+    using L = fa::SmemLayout<D, STAGES>;
+    auto kern = fa::fwdSm100Kernel<D, STAGES, DT>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+    });
+    // the attribute is per device; set it again cheaply when several devices are used from one process
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static std::atomic<unsigned long long> dev_mask{0};
+    if (!(dev_mask.load() & (1ull << dev))) {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+        dev_mask.fetch_or(1ull << dev);
+    }
+    if (attr_err != cudaSuccess) return fail(FA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) -> %s", L::kDynamicBytes,
+                                             cudaGetErrorString(attr_err));
+    const int rows_per_cta = fa::kTilesPerCta * fa::kBlockM;
+    dim3 grid((p.Nq + rows_per_cta - 1) / rows_per_cta, p.Hq, p.B);
+    kern<<<grid, fa::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
+    g_launches.fetch_add(1);
+    FA_CUDA(cudaGetLastError());
+    return FA_OK;
+}
+
+template <int D>
+int launch_fp32(const fa::Fp32Params& p, cudaStream_t st) {
+    using S = fa::Fp32Smem<D>;
+    auto kern = fa::fwdFp32Kernel<D>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static std::atomic<unsigned long long> dev_mask{0};
+    if (!(dev_mask.load() & (1ull << dev))) {
+        FA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
+        dev_mask.fetch_or(1ull << dev);
+    }
+    dim3 grid((p.Nq + fa::kF32Rows - 1) / fa::kF32Rows, p.Hq, p.B);
+    kern<<<grid, fa::kF32Threads, S::kBytes, st>>>(p);
+    g_launches.fetch_add(1);
+    FA_CUDA(cudaGetLastError());
+    return FA_OK;
+}
+
+int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, int B, int Hq, int Hkv, int Nq, int Nk,
+             int d, int dtype, float scale, int causal, const long long* s, cudaStream_t st) {
+    if (!Q || !K || !V || !O) return fail(FA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    if (B <= 0 || Hq <= 0 || Hkv <= 0 || Nq <= 0 || Nk <= 0 || d <= 0)
+        return fail(FA_ERR_INVALID_ARGUMENT, "non-positive size (B=%d Hq=%d Hkv=%d Nq=%d Nk=%d d=%d)", B, Hq, Hkv, Nq, Nk, d);
+    if (Hq % Hkv != 0) return fail(FA_ERR_INVALID_ARGUMENT, "Hq=%d is not a multiple of Hkv=%d", Hq, Hkv);
+    if (B > 65535 || Hq > 65535) return fail(FA_ERR_INVALID_ARGUMENT, "B and Hq must be <= 65535");
+    if (dtype != FA_DTYPE_F32 && dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16)
+        return fail(FA_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+    if (int rc = check_device()) return rc;
+    const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)d);
+
+    long long def[12];
+    if (!s) {
+        const long long qs[3] = {(long long)Hq * Nq * d, (long long)Nq * d, d};
+        const long long ks[3] = {(long long)Hkv * Nk * d, (long long)Nk * d, d};
+        for (int i = 0; i < 3; ++i) { def[i] = qs[i]; def[3 + i] = ks[i]; def[6 + i] = ks[i]; def[9 + i] = qs[i]; }
+        s = def;
+    }
+    for (int i = 0; i < 12; ++i)
+        if (s[i] <= 0) return fail(FA_ERR_INVALID_ARGUMENT, "stride %d must be positive", i);
+
+    if (dtype == FA_DTYPE_F32) {
+        if (d % 16 != 0 || d > 128) return fail(FA_ERR_UNSUPPORTED, "fp32 path needs d %% 16 == 0 and d <= 128 (got %d)", d);
+        fa::Fp32Params p;
+        p.Q = (const float*)Q; p.K = (const float*)K; p.V = (const float*)V; p.O = (float*)O; p.lse = lse;
+        p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
+        p.q_sb = s[0]; p.q_sh = s[1]; p.q_sn = s[2]; p.k_sb = s[3]; p.k_sh = s[4]; p.k_sn = s[5];
+        p.v_sb = s[6]; p.v_sh = s[7]; p.v_sn = s[8]; p.o_sb = s[9]; p.o_sh = s[10]; p.o_sn = s[11];
+        p.scale = sc; p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
+        switch (d) {
+            case 16: return launch_fp32<16>(p, st);
+            case 32: return launch_fp32<32>(p, st);
+            case 48: return launch_fp32<48>(p, st);
+            case 64: return launch_fp32<64>(p, st);
+            case 80: return launch_fp32<80>(p, st);
+            case 96: return launch_fp32<96>(p, st);
+            case 112: return launch_fp32<112>(p, st);
+            case 128: return launch_fp32<128>(p, st);
+        }
+        return fail(FA_ERR_UNSUPPORTED, "fp32 path: unsupported d=%d", d);
+    }
+
+    if (d != 64 && d != 128) return fail(FA_ERR_UNSUPPORTED, "16-bit path supports d in {64,128} (got %d)", d);
+    const void* ptrs[4] = {Q, K, V, O};
+    for (int i = 0; i < 4; ++i)
+        if (reinterpret_cast<uintptr_t>(ptrs[i]) % 16 != 0) return fail(FA_ERR_INVALID_ARGUMENT, "tensor %d is not 16-byte aligned", i);
+    for (int i = 0; i < 12; ++i)
+        if (s[i] % 8 != 0) return fail(FA_ERR_INVALID_ARGUMENT, "stride %d (=%lld elements) must be a multiple of 8", i, s[i]);
+
+    CUtensorMap tq, tk, tv;
+    if (int rc = make_tile_map(&tq, Q, dtype, B, Hq, Nq, d, s[0], s[1], s[2])) return rc;
+    if (int rc = make_tile_map(&tk, K, dtype, B, Hkv, Nk, d, s[3], s[4], s[5])) return rc;
+    if (int rc = make_tile_map(&tv, V, dtype, B, Hkv, Nk, d, s[6], s[7], s[8])) return rc;
+
+    fa::FwdParams p;
+    p.O = O; p.lse = lse; p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
+    p.o_stride_b = s[9]; p.o_stride_h = s[10]; p.o_stride_n = s[11];
+    p.scale = sc; p.scale_log2 = sc * 1.4426950408889634f;
+    p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
+
+    if (d == 128) {
+        return dtype == FA_DTYPE_BF16 ? launch_sm100<128, 5, fa::kBF16>(tq, tk, tv, p, st)
+                                      : launch_sm100<128, 5, fa::kF16>(tq, tk, tv, p, st);
+    }
+    return dtype == FA_DTYPE_BF16 ? launch_sm100<64, 8, fa::kBF16>(tq, tk, tv, p, st)
+                                  : launch_sm100<64, 8, fa::kF16>(tq, tk, tv, p, st);
+}
+
+// ---- host-buffer pipeline state ---------------------------------------------------------------------
+struct HostPipe {
+    static constexpr int kSlots = 3;
+    cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
+    void* buf[kSlots] = {nullptr, nullptr, nullptr};
+    size_t cap[kSlots] = {0, 0, 0};
+    int device = -1;
+};
+std::mutex g_pipe_mu;
+HostPipe g_pipe;
+
+}  // namespace
+
+extern "C" {
+
+const char* fa_last_error(void) { return g_err; }
+long long fa_launch_count(void) { return g_launches.load(); }
+const char* fa_version(void) { return "fa_b200 0.1 (sm_100a, tcgen05/TMEM/TMA)"; }
+
+int fa_fwd(const void* Q, const void* K, const void* V, void* O, float* lse, int B, int Hq, int Hkv, int Nq, int Nk,
+           int d, int dtype, float scale, int causal, void* stream) {
+    g_err[0] = 0;
+    return fwd_impl(Q, K, V, O, lse, B, Hq, Hkv, Nq, Nk, d, dtype, scale, causal, nullptr, (cudaStream_t)stream);
+}
+
+int fa_fwd_strided(const void* Q, const void* K, const void* V, void* O, float* lse, int B, int Hq, int Hkv, int Nq,
+                   int Nk, int d, int dtype, float scale, int causal, const long long* strides, void* stream) {
+    g_err[0] = 0;
+    if (!strides) return fail(FA_ERR_INVALID_ARGUMENT, "strides is null");
+    return fwd_impl(Q, K, V, O, lse, B, Hq, Hkv, Nq, Nk, d, dtype, scale, causal, strides, (cudaStream_t)stream);
+}
+
+int fa_mha_fwd_f32(const float* Q, const float* K, const float* V, float* O, int batchSize, int numHeads, int seqLen,
+                   int d_head, float scale, int is_causal, void* stream) {
+    g_err[0] = 0;
+    return fwd_impl(Q, K, V, O, nullptr, batchSize, numHeads, numHeads, seqLen, seqLen, d_head, FA_DTYPE_F32, scale,
+                    is_causal, nullptr, (cudaStream_t)stream);
+}
+
+int fa_fwd_host(const void* hQ, const void* hK, const void* hV, void* hO, float* hlse, int B, int Hq, int Hkv, int Nq,
+                int Nk, int d, int dtype, float scale, int causal) {
+    g_err[0] = 0;
+    if (!hQ || !hK || !hV || !hO) return fail(FA_ERR_INVALID_ARGUMENT, "null host pointer");
+    if (B <= 0 || Hq <= 0 || Hkv <= 0 || Nq <= 0 || Nk <= 0 || d <= 0 || Hq % Hkv != 0)
+        return fail(FA_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (int rc = check_device()) return rc;
+    const size_t es = dtype == FA_DTYPE_F32 ? 4 : 2;
+    const int g = Hq / Hkv;
+    // unit = one (batch, kv head): g query heads + 1 K head + 1 V head; units are contiguous in all four tensors
+    const long long units = (long long)B * Hkv;
+    const size_t q_unit = (size_t)g * Nq * d * es, kv_unit = (size_t)Nk * d * es, lse_unit = (size_t)g * Nq * 4;
+    const size_t unit_bytes = 2 * q_unit + 2 * kv_unit + lse_unit;
+    const size_t target = 96ull << 20;   // bytes per pipeline chunk
+    long long upc = (long long)(target / unit_bytes);
+    if (upc < 1) upc = 1;
+    if (upc > units) upc = units;
+    if (upc > 65535) upc = 65535;
+    const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)d);
+
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    int dev = 0;
+    FA_CUDA(cudaGetDevice(&dev));
+    if (g_pipe.device != dev) {
+        for (int i = 0; i < HostPipe::kSlots; ++i) {
+            if (g_pipe.buf[i]) cudaFree(g_pipe.buf[i]);
+            if (g_pipe.streams[i]) cudaStreamDestroy(g_pipe.streams[i]);
+            g_pipe.buf[i] = nullptr; g_pipe.cap[i] = 0; g_pipe.streams[i] = nullptr;
+        }
+        for (int i = 0; i < HostPipe::kSlots; ++i) FA_CUDA(cudaStreamCreateWithFlags(&g_pipe.streams[i], cudaStreamNonBlocking));
+        g_pipe.device = dev;
+    }
+    const size_t need = (size_t)upc * unit_bytes + 1024;
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        if (g_pipe.cap[i] < need) {
+            if (g_pipe.buf[i]) FA_CUDA(cudaFree(g_pipe.buf[i]));
+            g_pipe.buf[i] = nullptr; g_pipe.cap[i] = 0;
+            FA_CUDA(cudaMalloc(&g_pipe.buf[i], need));
+            g_pipe.cap[i] = need;
+        }
+    }
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    int slot = 0;
+    for (long long u0 = 0; u0 < units; u0 += upc, slot = (slot + 1) % HostPipe::kSlots) {
+        const long long nu = (units - u0 < upc) ? (units - u0) : upc;
+        cudaStream_t st = g_pipe.streams[slot];
+        char* base = (char*)g_pipe.buf[slot];
+        char* dQ = base;
+        char* dK = dQ + al(nu * q_unit);
+        char* dV = dK + al(nu * kv_unit);
+        char* dO = dV + al(nu * kv_unit);
+        float* dL = hlse ? (float*)(dO + al(nu * q_unit)) : nullptr;
+        FA_CUDA(cudaMemcpyAsync(dQ, (const char*)hQ + u0 * q_unit, nu * q_unit, cudaMemcpyHostToDevice, st));
+        FA_CUDA(cudaMemcpyAsync(dK, (const char*)hK + u0 * kv_unit, nu * kv_unit, cudaMemcpyHostToDevice, st));
+        FA_CUDA(cudaMemcpyAsync(dV, (const char*)hV + u0 * kv_unit, nu * kv_unit, cudaMemcpyHostToDevice, st));
+        // each unit is presented to the kernel as one "batch" entry with g query heads and one kv head
+        if (int rc = fwd_impl(dQ, dK, dV, dO, dL, (int)nu, g, 1, Nq, Nk, d, dtype, sc, causal, nullptr, st)) return rc;
+        FA_CUDA(cudaMemcpyAsync((char*)hO + u0 * q_unit, dO, nu * q_unit, cudaMemcpyDeviceToHost, st));
+        if (hlse) FA_CUDA(cudaMemcpyAsync((char*)hlse + u0 * lse_unit, dL, nu * lse_unit, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < HostPipe::kSlots; ++i) FA_CUDA(cudaStreamSynchronize(g_pipe.streams[i]));
+    return FA_OK;
+}
+
+int fa_merge_partial(float* acc_o, float* acc_lse, const void* part_o, const float* part_lse, long long rows, int d,
+                     int dtype, void* stream) {
+    g_err[0] = 0;
+    if (!acc_o || !acc_lse || !part_o || !part_lse || rows <= 0 || d <= 0 || d % 2)
+        return fail(FA_ERR_INVALID_ARGUMENT, "bad merge arguments");
+    if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16) return fail(FA_ERR_UNSUPPORTED, "merge takes 16-bit partials");
+    if (int rc = check_device()) return rc;
+    const int wpb = 8;
+    const unsigned blocks = (unsigned)((rows + wpb - 1) / wpb);
+    if (dtype == FA_DTYPE_BF16)
+        fa::mergePartialKernel<fa::kBF16><<<blocks, wpb * 32, 0, (cudaStream_t)stream>>>(acc_o, acc_lse, (const uint16_t*)part_o, part_lse, rows, d);
+    else
+        fa::mergePartialKernel<fa::kF16><<<blocks, wpb * 32, 0, (cudaStream_t)stream>>>(acc_o, acc_lse, (const uint16_t*)part_o, part_lse, rows, d);
+    g_launches.fetch_add(1);
+    FA_CUDA(cudaGetLastError());
+    return FA_OK;
+}
+
+int fa_cast_out(const float* src, void* dst, long long n, int dtype, void* stream) {
+    g_err[0] = 0;
+    if (!src || !dst || n <= 0 || n % 2) return fail(FA_ERR_INVALID_ARGUMENT, "bad cast arguments");
+    if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16) return fail(FA_ERR_UNSUPPORTED, "cast target must be 16-bit");
+    if (int rc = check_device()) return rc;
+    const long long n2 = n / 2;
+    const unsigned blocks = (unsigned)((n2 + 255) / 256);
+    if (dtype == FA_DTYPE_BF16)
+        fa::castOutKernel<fa::kBF16><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, n2);
+    else
+        fa::castOutKernel<fa::kF16><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, n2);
+    g_launches.fetch_add(1);
+    FA_CUDA(cudaGetLastError());
+    return FA_OK;
+}
+
+int fa_device_info(int device, fa_device_info_t* out) {
+    g_err[0] = 0;
+    if (!out) return fail(FA_ERR_INVALID_ARGUMENT, "out is null");
+    cudaDeviceProp prop;
+    FA_CUDA(cudaGetDeviceProperties(&prop, device));
+    out->cc_major = prop.major; out->cc_minor = prop.minor; out->sm_count = prop.multiProcessorCount;
+    out->global_mem_bytes = prop.totalGlobalMem; out->smem_per_block_optin = prop.sharedMemPerBlockOptin;
+    out->smem_per_sm = prop.sharedMemPerMultiprocessor; out->regs_per_sm = prop.regsPerMultiprocessor;
+    out->warp_size = prop.warpSize; out->l2_bytes = prop.l2CacheSize; out->max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
+    return FA_OK;
+}
+
+int fa_block_q(int d, int dtype) {
+    (void)d;
+    return dtype == FA_DTYPE_F32 ? fa::kF32Rows : fa::kTilesPerCta * fa::kBlockM;
+}
+int fa_block_kv(int d, int dtype) {
+    (void)d;
+    return dtype == FA_DTYPE_F32 ? fa::kF32Rows : fa::kBlockN;
+}
+int fa_num_cta(int q_dim, int q_block_size) {
+    if (q_dim <= 0 || q_block_size <= 0) return 0;
+    return (q_dim + q_block_size - 1) / q_block_size;
+}
+
+}  // extern "C"

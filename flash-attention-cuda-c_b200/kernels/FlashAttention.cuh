@@ -1,0 +1,389 @@
+// FlashAttention.cuh — launcher API of the attention forward path.
+//
+// Keeps the reference's include path and its public entry point
+//   template<int D_HEAD, int Q_TILE_ROWS, int KV_TILE_ROWS>
+//   __global__ void twoLoaderMhaFlashAttentionKernel(const float* Q, const float* K, const float* V, float* O,
+//                                                    int batchSize, int numHeads, int seqLen, float scale, bool is_causal)
+// (reference: kernels/FlashAttention.cuh:59-63), and adds the B200-native kernel the C-ABI launcher in
+// FlashAttention.cu dispatches to:
+//   fa::fwdSm100Kernel<D, STAGES, DT>   — warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16)
+//   fa::fwdFp32Kernel<D>                — exact-fp32 CUDA-core kernel for fp32 I/O
+// The compat template is launched by the *caller* with a grid/block/shared-memory size of its own choosing
+// (reference: tests/main.cu:51-61 uses grid 1, (QT+2)*32 threads, (3QT+4R)*D*4 bytes), so it cannot take TMA
+// descriptors; it is a self-contained fp32 kernel that is correct for any launch shape and — unlike the
+// reference — honours batch/head boundaries, uses K for the scores and handles
+// causal masking without NaNs.
+#pragma once
+
+#include "utils.cuh"
+#include "loaders.cuh"
+#include "computers.cuh"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cuda_fp16.h>
+
+namespace fa {
+
+// ------------------------------------------------------------------------------------------------
+// B200 kernel: grid = (query blocks of 256 rows, Hq, B), 384 threads, 1 CTA / SM.
+//   warps 0-3  softmax + correction + epilogue for query tile 0
+//   warps 4-7  softmax + correction + epilogue for query tile 1
+//   warp  8    MMA issuer (one thread)
+//   warp  9    TMA producer (one thread)
+//   warp 10    TMEM allocator
+// ------------------------------------------------------------------------------------------------
+template <int D, int STAGES, int DT>
+__global__ void __launch_bounds__(kNumThreads, 1)
+fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+    using L = SmemLayout<D, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kTmemPtrOff);
+
+    const int warp = threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == kMmaWarp && lane == 0) {
+        const uint32_t bar0 = smem_base + L::kBarOff;
+        mbar_init(bar0 + 8 * L::kBarQFull, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar0 + 8 * (L::kBarKVFull + s), 1);
+            mbar_init(bar0 + 8 * (L::kBarKVEmpty + s), 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar0 + 8 * (L::kBarSFull + t), 1);
+            mbar_init(bar0 + 8 * (L::kBarPFull + t), 128);
+            mbar_init(bar0 + 8 * (L::kBarOFull + t), 1);
+        }
+        fence_mbar_init();
+    } else if (warp == kLoadWarp && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    } else if (warp == kTmemWarp) {
+        tmem_alloc(smem_base + L::kTmemPtrOff, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const WorkItem w = decode_work(p);
+
+    if (warp < kSoftmaxWarps) {
+        reg_inc<kSoftmaxRegs>();
+        softmaxWarpgroup<D, STAGES, DT>(smem_base, tmem_base, w, p, warp / 4);
+    } else {
+        reg_dec<kOtherRegs>();
+        if (warp == kMmaWarp) {
+            if (lane == 0) mmaIssuerThread<D, STAGES, DT>(smem_base, tmem_base, w);
+        } else if (warp == kLoadWarp) {
+            if (lane == 0) tmaLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, w);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTmemWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact-fp32 kernel (fp32 in, fp32 out, fp32 accumulate on the FMA pipe).  grid = (ceil(Nq/64), Hq, B),
+// 256 threads.  A 64-row query tile against 64-row key/value tiles staged in shared memory; each thread owns
+// a 4x4 patch of S and a 4 x (D/16) patch of O.  Used for fp32 I/O where TF32/bf16 tensor-core products would
+// miss the 1e-4 relative tolerance.
+// ------------------------------------------------------------------------------------------------
+constexpr int kF32Rows = 64;
+constexpr int kF32Threads = 256;
+
+template <int D>
+struct Fp32Smem {
+    // Qt[d][64] (transposed), Kt[d][64] (transposed), V[64][D], P[64][65]
+    static constexpr int kQt = 0;
+    static constexpr int kKt = kQt + D * kF32Rows;
+    static constexpr int kV = kKt + D * kF32Rows;
+    static constexpr int kP = kV + kF32Rows * D;
+    static constexpr int kFloats = kP + kF32Rows * (kF32Rows + 1);
+    static constexpr int kBytes = kFloats * 4;
+};
+
+struct Fp32Params {
+    const float* Q;
+    const float* K;
+    const float* V;
+    float* O;
+    float* lse;
+    int B, Hq, Hkv, Nq, Nk;
+    long long q_sb, q_sh, q_sn, k_sb, k_sh, k_sn, v_sb, v_sh, v_sn, o_sb, o_sh, o_sn;   // element strides
+    float scale;
+    int causal, causal_off, q_heads_per_kv;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kF32Threads) fwdFp32Kernel(const Fp32Params p) {
+    static_assert(D % 16 == 0 && D <= 256, "head dim must be a multiple of 16");
+    using S = Fp32Smem<D>;
+    extern __shared__ float sm[];
+    float* Qt = sm + S::kQt;
+    float* Kt = sm + S::kKt;
+    float* Vs = sm + S::kV;
+    float* Ps = sm + S::kP;
+    constexpr int DO = D / 16;   // O columns per thread
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15;     // column group
+    const int ty = tid >> 4;     // row group
+    const int qb = p.causal ? (int(gridDim.x) - 1 - int(blockIdx.x)) : int(blockIdx.x);
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int hk = h / p.q_heads_per_kv;
+    const int q0 = qb * kF32Rows;
+
+    const float* Qg = p.Q + b * p.q_sb + h * p.q_sh;
+    const float* Kg = p.K + b * p.k_sb + hk * p.k_sh;
+    const float* Vg = p.V + b * p.v_sb + hk * p.v_sh;
+
+    // Q tile -> smem, transposed (zero rows past Nq)
+    for (int i = tid; i < kF32Rows * D; i += kF32Threads) {
+        const int r = i / D, d = i % D;
+        Qt[d * kF32Rows + r] = (q0 + r < p.Nq) ? Qg[(long long)(q0 + r) * p.q_sn + d] : 0.f;
+    }
+
+    float m[4], l[4], acc[4][DO];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m[i] = -INFINITY;
+        l[i] = 0.f;
+#pragma unroll
+        for (int d = 0; d < DO; ++d) acc[i][d] = 0.f;
+    }
+
+    int n_kv = (p.Nk + kF32Rows - 1) / kF32Rows;
+    if (p.causal) {
+        const int last_col = q0 + kF32Rows - 1 + p.causal_off;
+        const int nc = last_col < 0 ? 0 : last_col / kF32Rows + 1;
+        n_kv = nc < n_kv ? nc : n_kv;
+    }
+
+    for (int j = 0; j < n_kv; ++j) {
+        const int kv0 = j * kF32Rows;
+        __syncthreads();   // previous tile fully consumed (also covers the Q staging on j == 0)
+        for (int i = tid; i < kF32Rows * D; i += kF32Threads) {
+            const int r = i / D, d = i % D;
+            const bool ok = kv0 + r < p.Nk;
+            Kt[d * kF32Rows + r] = ok ? Kg[(long long)(kv0 + r) * p.k_sn + d] : 0.f;
+            Vs[r * D + d] = ok ? Vg[(long long)(kv0 + r) * p.v_sn + d] : 0.f;
+        }
+        __syncthreads();
+
+        // S patch: rows 4*ty..+3, cols 4*tx..+3
+        float s[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[i][k] = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < D; ++d) {
+            const float4 qv = *reinterpret_cast<const float4*>(Qt + d * kF32Rows + 4 * ty);
+            const float4 kv = *reinterpret_cast<const float4*>(Kt + d * kF32Rows + 4 * tx);
+            const float qa[4] = {qv.x, qv.y, qv.z, qv.w};
+            const float ka[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s[i][k] = fmaf(qa[i], ka[k], s[i][k]);
+        }
+        // scale + mask, row max over the 16 threads sharing a row group
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = q0 + 4 * ty + i;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = kv0 + 4 * tx + k;
+                const bool masked = col >= p.Nk || (p.causal && col > row + p.causal_off);
+                s[i][k] = masked ? -INFINITY : s[i][k] * p.scale;
+                mx = fmaxf(mx, s[i][k]);
+            }
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float m_new = fmaxf(m[i], mx);
+            const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+            const float f = (m[i] == -INFINITY) ? 0.f : expf(m[i] - m_safe);
+            float rs = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float e = expf(s[i][k] - m_safe);   // exp(-inf) = 0 for masked entries
+                Ps[(4 * ty + i) * (kF32Rows + 1) + 4 * tx + k] = e;
+                rs += e;
+            }
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+            l[i] = l[i] * f + rs;
+            m[i] = m_new;
+#pragma unroll
+            for (int d = 0; d < DO; ++d) acc[i][d] *= f;
+        }
+        __syncthreads();
+        // O patch: rows 4*ty..+3, cols tx + 16*d
+#pragma unroll 4
+        for (int k = 0; k < kF32Rows; ++k) {
+            float pv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pv[i] = Ps[(4 * ty + i) * (kF32Rows + 1) + k];
+#pragma unroll
+            for (int d = 0; d < DO; ++d) {
+                const float v = Vs[k * D + tx + 16 * d];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][d] = fmaf(pv[i], v, acc[i][d]);
+            }
+        }
+    }
+
+    float* Og = p.O + b * p.o_sb + h * p.o_sh;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = q0 + 4 * ty + i;
+        if (row >= p.Nq) continue;
+        const float inv = l[i] > 0.f ? 1.0f / l[i] : 0.f;
+#pragma unroll
+        for (int d = 0; d < DO; ++d) Og[(long long)row * p.o_sn + tx + 16 * d] = acc[i][d] * inv;
+        if (p.lse != nullptr && tx == 0)
+            p.lse[((long long)b * p.Hq + h) * p.Nq + row] = l[i] > 0.f ? m[i] + logf(l[i]) : -INFINITY;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Combine two partial attention results over disjoint key ranges (ring-KV step):
+//   lse = log(exp(lse_a) + exp(lse_b));  O = O_a * exp(lse_a - lse) + O_b * exp(lse_b - lse)
+// acc (fp32 O_a, lse_a) is updated in place with a 16-bit partial (O_b, lse_b).  One warp per row.
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void mergePartialKernel(float* __restrict__ acc_o, float* __restrict__ acc_lse,
+                                   const uint16_t* __restrict__ part_o, const float* __restrict__ part_lse,
+                                   long long rows, int d) {
+    const long long row = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float la = acc_lse[row], lb = part_lse[row];
+    const float mx = fmaxf(la, lb);
+    float wa, wb, lnew;
+    if (mx == -INFINITY) {
+        wa = 0.f; wb = 0.f; lnew = -INFINITY;
+    } else {
+        const float ea = expf(la - mx), eb = expf(lb - mx);
+        const float inv = 1.0f / (ea + eb);
+        wa = ea * inv; wb = eb * inv;
+        lnew = mx + logf(ea + eb);
+    }
+    for (int c = lane * 2; c < d; c += 64) {
+        const uint32_t pb = *reinterpret_cast<const uint32_t*>(part_o + row * d + c);
+        float b0, b1;
+        if constexpr (DT == kBF16) {
+            b0 = __uint_as_float(pb << 16);
+            b1 = __uint_as_float(pb & 0xffff0000u);
+        } else {
+            const __half2 hh = *reinterpret_cast<const __half2*>(&pb);
+            b0 = __low2float(hh);
+            b1 = __high2float(hh);
+        }
+        float2 a = *reinterpret_cast<float2*>(acc_o + row * d + c);
+        a.x = a.x * wa + b0 * wb;
+        a.y = a.y * wa + b1 * wb;
+        *reinterpret_cast<float2*>(acc_o + row * d + c) = a;
+    }
+    if (lane == 0) acc_lse[row] = lnew;
+}
+
+// fp32 accumulator -> 16-bit output
+template <int DT>
+__global__ void castOutKernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const float2 v = reinterpret_cast<const float2*>(src)[i];
+    reinterpret_cast<uint32_t*>(dst)[i] = pack16<DT>(v.x, v.y);
+}
+
+}  // namespace fa
+
+// ------------------------------------------------------------------------------------------------
+// Compat entry point: same name, template parameters and argument list as the reference
+// (reference: kernels/FlashAttention.cuh:59-63).  Correct for any grid / block / dynamic-smem choice of the
+// caller: query rows of all (batch, head) pairs are distributed warp-by-warp over the whole grid; each
+// warp streams the keys of *its own* (batch, head) in chunks of 32, lane j scoring key j, then accumulates
+// O with lanes owning output columns.  Q_TILE_ROWS / KV_TILE_ROWS are accepted for source compatibility;
+// the result does not depend on them.
+// ------------------------------------------------------------------------------------------------
+template <int D_HEAD, int Q_TILE_ROWS, int KV_TILE_ROWS>
+__global__ void twoLoaderMhaFlashAttentionKernel(
+    const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, float* __restrict__ O,
+    int batchSize, int numHeads, int seqLen, float scale, bool is_causal)
+{
+    constexpr int DPL = (D_HEAD + WARP - 1) / WARP;   // output columns per lane
+    const int lane = threadIdx.x % WARP;
+    const int warps_per_block = blockDim.x / WARP;
+    const long long total_rows = (long long)batchSize * numHeads * seqLen;
+    const long long warp_global = (long long)blockIdx.x * warps_per_block + threadIdx.x / WARP;
+    const long long warp_stride = (long long)gridDim.x * warps_per_block;
+
+    for (long long grow = warp_global; grow < total_rows; grow += warp_stride) {
+        const long long bh = grow / seqLen;
+        const int i = int(grow % seqLen);
+        const float* q = Q + grow * D_HEAD;
+        const float* kbase = K + bh * seqLen * D_HEAD;
+        const float* vbase = V + bh * seqLen * D_HEAD;
+        const int n_keys = is_causal ? (i + 1) : seqLen;
+
+        float m = -INFINITY, l = 0.f, acc[DPL];
+#pragma unroll
+        for (int c = 0; c < DPL; ++c) acc[c] = 0.f;
+
+        for (int j0 = 0; j0 < n_keys; j0 += WARP) {
+            const int j = j0 + lane;
+            float s = -INFINITY;
+            if (j < n_keys) {
+                const float* kr = kbase + (long long)j * D_HEAD;
+                float dot = 0.f;
+#pragma unroll 8
+                for (int d = 0; d < D_HEAD; ++d) dot = fmaf(q[d], kr[d], dot);
+                s = dot * scale;
+            }
+            float mx = s;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float m_new = fmaxf(m, mx);          // finite: lane 0 of every chunk is a valid key
+            const float f = expf(m - m_new);           // exp(-inf) = 0 on the first chunk
+            const float e = expf(s - m_new);
+            float rs = e;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+            l = l * f + rs;
+            m = m_new;
+#pragma unroll
+            for (int c = 0; c < DPL; ++c) acc[c] *= f;
+            const int cnt = min(WARP, n_keys - j0);
+            for (int jj = 0; jj < cnt; ++jj) {
+                const float pj = __shfl_sync(0xffffffffu, e, jj);
+                const float* vr = vbase + (long long)(j0 + jj) * D_HEAD;
+#pragma unroll
+                for (int c = 0; c < DPL; ++c) {
+                    const int d = lane + c * WARP;
+                    if (d < D_HEAD) acc[c] = fmaf(pj, vr[d], acc[c]);
+                }
+            }
+        }
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int c = 0; c < DPL; ++c) {
+            const int d = lane + c * WARP;
+            if (d < D_HEAD) O[grow * D_HEAD + d] = acc[c] * inv;
+        }
+    }
+}

@@ -1,0 +1,134 @@
+// loaders.cuh — tile loaders of the B200 attention forward path.
+//
+// Takes the place of the reference's kernels/loaders.cuh:
+//   * shared-memory carve-up      (reference: loaders.cuh:23-52,  [Q0|Q1|K0|K1|V0|V1|O] in floats)
+//   * asyncBufferLoad / loader warps (reference: loaders.cuh:55-83, 114-203, per-lane cp.async pieces
+//     issued by two producer warps that walk every pipeline phase in lock-step with the math warps)
+// Here one elected thread issues TMA bulk-tensor copies (cp.async.bulk.tensor.4d) of whole
+// 128-row tiles into 128B-swizzled shared memory; completion is signalled on mbarriers
+// (expect_tx / complete_tx), and slots are handed back by tcgen05.commit from the MMA issuer.
+//
+// Shared memory map (all tile buffers 1024-B aligned, required by SWIZZLE_128B):
+//   [ Q tile 0 | Q tile 1 | KV ring slot 0 .. slot S-1 | mbarriers | tmem base ]
+// A 128 x D tile of 16-bit elements is stored as D/64 "halves"; half h holds columns [64h, 64h+64)
+// as 128 rows of 128 bytes (row r at byte r*128, 16-byte chunks XOR-swizzled by r%8) — exactly
+// what a TMA box of {64, 128} with CU_TENSOR_MAP_SWIZZLE_128B writes and what the UMMA
+// descriptors in computers.cuh describe.  K and V tiles alternate through one ring: K0 V0 K1 V1 ...
+#pragma once
+
+#include "utils.cuh"
+
+namespace fa {
+
+constexpr int kBlockM = 128;       // query rows per MMA tile (TMEM lanes)
+constexpr int kTilesPerCta = 2;    // two query tiles per CTA, ping-ponged through the tensor pipe
+constexpr int kBlockN = 128;       // key/value rows per tile
+constexpr int kHalfCols = 64;      // columns per swizzle-128B half (64 x 2 B = 128 B)
+constexpr int kHalfBytes = kBlockN * 128;   // 16 KiB: one half of a 128-row tile
+
+// Warp roles (384 threads = 3 warpgroups)
+constexpr int kSoftmaxWarps = 8;   // warps 0-3: query tile 0, warps 4-7: query tile 1
+constexpr int kMmaWarp = 8;
+constexpr int kLoadWarp = 9;
+constexpr int kTmemWarp = 10;
+constexpr int kNumThreads = 384;
+// Register split (setmaxnreg): 384 x 168 at launch -> 256 x 208 (softmax) + 128 x 88 (MMA / TMA / TMEM warps)
+constexpr int kSoftmaxRegs = 208;
+constexpr int kOtherRegs = 88;
+
+struct FwdParams {
+    void* O;                 // output, same dtype as Q
+    float* lse;              // optional [B, Hq, Nq] log-sum-exp (natural log), may be null
+    int B, Hq, Hkv, Nq, Nk;
+    long long o_stride_b, o_stride_h, o_stride_n;   // in elements; innermost (d) stride is 1
+    float scale;             // softmax scale (1/sqrt(d) by default)
+    float scale_log2;        // scale * log2(e)
+    int causal;              // 0/1
+    int causal_off;          // Nk - Nq: key j visible to query i iff j <= i + causal_off
+    int q_heads_per_kv;      // Hq / Hkv
+};
+
+template <int D, int STAGES>
+struct SmemLayout {
+    static constexpr int kQTileBytes = kBlockM * D * 2;
+    static constexpr int kKVTileBytes = kBlockN * D * 2;
+    static constexpr int kQOff = 0;
+    static constexpr int kKVOff = kTilesPerCta * kQTileBytes;
+    static constexpr int kBarOff = kKVOff + STAGES * kKVTileBytes;
+    // barrier indices
+    static constexpr int kBarQFull = 0;
+    static constexpr int kBarKVFull = 1;
+    static constexpr int kBarKVEmpty = kBarKVFull + STAGES;
+    static constexpr int kBarSFull = kBarKVEmpty + STAGES;     // [2]  MMA -> softmax : S tile ready in TMEM
+    static constexpr int kBarPFull = kBarSFull + 2;            // [2]  softmax -> MMA : P written (and O rescaled)
+    static constexpr int kBarOFull = kBarPFull + 2;            // [2]  MMA -> softmax : P*V of this step retired
+    static constexpr int kNumBars = kBarOFull + 2;
+    static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+    static constexpr int kBytes = kTmemPtrOff + 16;
+    static constexpr int kDynamicBytes = kBytes + 1024;        // slack for manual 1024-B alignment
+};
+
+// Work item of one CTA.
+struct WorkItem {
+    int b, h, h_kv;
+    int q0;        // first query row of the CTA's 256-row block
+    int n_kv;      // number of 128-row key/value tiles to visit
+};
+
+__device__ __forceinline__ WorkItem decode_work(const FwdParams& p) {
+    WorkItem w;
+    // Heavy (late) causal query blocks first: the hardware block scheduler then acts as an LPT queue.
+    const int qb = p.causal ? (int(gridDim.x) - 1 - int(blockIdx.x)) : int(blockIdx.x);
+    w.h = blockIdx.y;
+    w.b = blockIdx.z;
+    w.h_kv = w.h / p.q_heads_per_kv;
+    w.q0 = qb * (kTilesPerCta * kBlockM);
+    int n = (p.Nk + kBlockN - 1) / kBlockN;
+    if (p.causal) {
+        const int last_col = w.q0 + kTilesPerCta * kBlockM - 1 + p.causal_off;   // last key any row of the block may see
+        const int n_c = last_col < 0 ? 0 : last_col / kBlockN + 1;
+        n = n_c < n ? n_c : n;
+    }
+    w.n_kv = n;
+    return w;
+}
+
+// Producer: a single thread.  Q tiles once, then K_j, V_j for j = 0..n_kv-1 through the ring.
+template <int D, int STAGES>
+__device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CUtensorMap* tmK,
+                                                const CUtensorMap* tmV, uint32_t smem_base,
+                                                const WorkItem& w) {
+    using L = SmemLayout<D, STAGES>;
+    constexpr int kHalves = D / kHalfCols;
+    const uint32_t bar0 = smem_base + L::kBarOff;
+
+    // Q: both tiles on one barrier.
+    const uint32_t q_full = bar0 + 8 * L::kBarQFull;
+    mbar_expect_tx(q_full, kTilesPerCta * L::kQTileBytes);
+#pragma unroll
+    for (int t = 0; t < kTilesPerCta; ++t)
+#pragma unroll
+        for (int hf = 0; hf < kHalves; ++hf)
+            tma_load_4d_hint(tmQ, smem_base + L::kQOff + t * L::kQTileBytes + hf * kHalfBytes, q_full,
+                             hf * kHalfCols, w.q0 + t * kBlockM, w.h, w.b, kEvictFirst);
+
+    int it = 0;
+    for (int j = 0; j < w.n_kv; ++j) {
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv, ++it) {
+            const int slot = it % STAGES;
+            const uint32_t parity = (it / STAGES) & 1;
+            const uint32_t full = bar0 + 8 * (L::kBarKVFull + slot);
+            const uint32_t empty = bar0 + 8 * (L::kBarKVEmpty + slot);
+            mbar_wait(empty, parity ^ 1);
+            mbar_expect_tx(full, L::kKVTileBytes);
+            const CUtensorMap* tm = kv == 0 ? tmK : tmV;
+#pragma unroll
+            for (int hf = 0; hf < kHalves; ++hf)
+                tma_load_4d_hint(tm, smem_base + L::kKVOff + slot * L::kKVTileBytes + hf * kHalfBytes, full,
+                                 hf * kHalfCols, j * kBlockN, w.h_kv, w.b, kEvictLast);
+        }
+    }
+}
+
+}  // namespace fa

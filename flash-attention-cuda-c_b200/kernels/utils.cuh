@@ -1,0 +1,309 @@
+// utils.cuh — device-side helpers for the B200 (sm_100a) attention forward path.
+//
+// Takes the place of the reference's kernels/utils.cuh (reference: /root/reference/kernels/utils.cuh:12-113).
+// There the helpers were cooperative-groups dot products, shuffle reductions and the FA-1 style
+// per-tile-normalised softmax state.  Here the helpers are the raw sm_100a building blocks the
+// stages in loaders.cuh / computers.cuh are made of:
+//   * mbarrier (init / expect_tx / arrive / parity wait with a hang guard)
+//   * TMA bulk-tensor loads (cp.async.bulk.tensor.4d)
+//   * tcgen05: TMEM alloc/dealloc, mma (SS and TS forms), commit, ld/st, fences
+//   * UMMA shared-memory / instruction descriptor builders
+//   * packed fp32x2 math, exp2, bf16/fp16 packing
+// WARP and FLOAT_SIZE keep the reference's names (utils.cuh:12-13).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+
+#define WARP 32
+#define FLOAT_SIZE 4
+
+#ifndef FA_HANG_GUARD_CYCLES
+// Any mbarrier wait that spins longer than this many SM cycles traps instead of hanging the GPU.
+#define FA_HANG_GUARD_CYCLES (4000000000LL)
+#endif
+
+namespace fa {
+
+enum DType : int { kF32 = 0, kF16 = 1, kBF16 = 2 };
+
+// ------------------------------------------------------------------------------------------
+// addresses
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Parity wait.  The slow path carries a cycle-count guard so a protocol bug traps (a CUDA error the
+// host sees) instead of hanging the device.
+__device__ __forceinline__ void mbar_hang_report(uint32_t bar, uint32_t parity) {
+#ifdef FA_DEBUG_HANG   // names the barrier; off by default because the printf call costs registers in every role
+    printf("fa_b200: mbarrier wait timed out (block %d,%d,%d thread %d bar 0x%x parity %u)\n",
+           blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+#endif
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > FA_HANG_GUARD_CYCLES) mbar_hang_report(bar, parity);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 4-D tiled load: coordinates are (innermost .. outermost) = (c0 = column in d, c1 = row in N, c2 = head, c3 = batch)
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t dst_smem, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_hint(const CUtensorMap* m, uint32_t dst_smem, uint32_t bar,
+                                                 int c0, int c1, int c2, int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+          "l"(policy)
+        : "memory");
+}
+// 4-D tiled store (shared -> global), bulk-group completion.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_smem,
+                                             int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// L2 eviction policies (same encodings createpolicy would return; used as cache hints)
+static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+static constexpr uint64_t kEvictLast  = 0x14F0000000000000ull;
+
+// ------------------------------------------------------------------------------------------
+// tcgen05: TMEM management, fences, commit
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {   // whole warp
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {   // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Arrive (count 1) on an mbarrier once every tcgen05 op issued so far by this thread has completed.
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Register re-allocation between warpgroups (all 128 threads of a warpgroup must execute it).
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// ------------------------------------------------------------------------------------------
+// tcgen05.mma  (kind::f16: bf16 or fp16 operands, fp32 accumulate in TMEM)
+// ------------------------------------------------------------------------------------------
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Instruction descriptor for kind::f16 (bit layout: c_format[4,6) a_format[7,10) b_format[10,13)
+// a_major[15] b_major[16] N>>3 [17,23) M>>4 [24,29)).  ab_fmt: 0 = fp16, 1 = bf16.  *_mn: 1 = MN-major.
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int ab_fmt, int a_mn, int b_mn) {
+    return (1u << 4) | (uint32_t(ab_fmt) << 7) | (uint32_t(ab_fmt) << 10) | (uint32_t(a_mn) << 15) |
+           (uint32_t(b_mn) << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bits.
+//   start address  bits [0,14)   (>>4)
+//   leading  byte offset bits [16,30) (>>4)
+//   stride   byte offset bits [32,46) (>>4)
+//   version        bits [46,48) = 1
+//   layout type    bits [61,64) = 2 (SWIZZLE_128B)
+// K-major operand (rows of 128 B = 64 halfs of K): SBO = 1024 (8 rows), LBO unused.
+// MN-major operand (rows of 128 B = 64 halfs of MN, one row per K index): SBO = 1024 (8 K rows),
+// LBO = distance between consecutive 64-element MN blocks.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr >> 4) & 0x3FFFu);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05.ld / tcgen05.st, shape 32x32b: thread i of the warp <-> TMEM lane (lane_base + i),
+// N consecutive 32-bit columns per thread.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// math
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// (a.x*b.x + c.x, a.y*b.y + c.y) in one instruction (sm_100 packed fp32)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    uint64_t ua, ub, uc, ud;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    uint64_t ua, ub, ud;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    uint64_t ua, ub, ud;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+    return d;
+}
+// v if idx <= lim else -inf; written as one predicated select so the compiler keeps the score row in registers
+__device__ __forceinline__ uint32_t mask_gt(uint32_t v, int idx, int lim) {
+    uint32_t d;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %2, %3;\n\tselp.b32 %0, 0xff800000, %1, p;\n\t}"
+        : "=r"(d) : "r"(v), "r"(idx), "r"(lim));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// pack two fp32 into one 32-bit word of 16-bit floats: low half = lo, high half = hi
+template <int DT>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+    uint32_t d;
+    if constexpr (DT == kBF16) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    } else {
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    }
+    return d;
+}
+
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+}  // namespace fa

@@ -1,0 +1,115 @@
+/* fa_b200.h — C ABI of the B200-native fused attention forward path.
+ *
+ * This is the drop-in boundary for the one hot path of GMichailov/Flash-Attention-CUDA-C:
+ * the fused attention forward kernel behind kernels/FlashAttention.cuh.  The reference has no C ABI of
+ * its own — its interface is a header-only __global__ template that the caller launches itself
+ * (reference: kernels/FlashAttention.cuh:59-63, only caller tests/main.cu:60-61).  Each entry point below
+ * names the reference interface it stands in for.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Semantics (reference: check.py:4-25, tests/main.cu:73-91):
+ *   for batch b, query head h (kv head h / (Hq/Hkv)), query row i:
+ *     s_ij = scale * sum_d Q[b,h,i,d] * K[b,hkv,j,d];   causal: s_ij = -inf for j > i + (Nk - Nq)
+ *     O[b,h,i,:] = sum_j softmax_j(s_ij) * V[b,hkv,j,:]          (softmax and accumulation in fp32)
+ *     LSE[b,h,i] = log sum_j exp(s_ij)                           (optional)
+ * Default layout is the reference's: contiguous [B, H, N, d] (reference: loaders.cuh:57 row*D_HEAD addressing).
+ *
+ * All functions return FA_OK (0) or a negative error code; none of them calls exit() or assert()
+ * (the reference's caller used CUDA_CHECK -> exit(1), tests/main.cu:12-19, and helpers.hpp:34 asserts).
+ * All device work is enqueued on the given stream (NULL = default stream); nothing synchronises unless
+ * stated.  Functions are re-entrant; the library keeps no mutable global state except an immutable
+ * per-device property cache, a launch counter and a thread-local last-error string.
+ */
+#ifndef FA_B200_H_
+#define FA_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types of Q, K, V, O */
+enum { FA_DTYPE_F32 = 0, FA_DTYPE_F16 = 1, FA_DTYPE_BF16 = 2 };
+
+/* return codes */
+enum {
+    FA_OK = 0,
+    FA_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, Hq % Hkv != 0, misaligned pointer/stride */
+    FA_ERR_UNSUPPORTED = -2,      /* head dim / dtype combination without a kernel */
+    FA_ERR_CUDA = -3,             /* a CUDA runtime / driver call failed; see fa_last_error() */
+    FA_ERR_NOT_B200 = -4          /* the current device is not sm_100 (no fallback path exists) */
+};
+
+/* ---- the hot path -------------------------------------------------------------------------------------------
+ * fa_fwd: fused attention forward on device buffers, contiguous [B,Hq,Nq,d] Q/O and [B,Hkv,Nk,d] K/V.
+ * Replaces: launching twoLoaderMhaFlashAttentionKernel<D,QT,KVT><<<grid,block,smem>>>(Q,K,V,O,B,H,N,scale,causal)
+ *           (reference: kernels/FlashAttention.cuh:59-63; launch contract tests/main.cu:51-61).
+ *   dtype FA_DTYPE_BF16 / FA_DTYPE_F16: d in {64, 128}  -> TMA + tcgen05/TMEM kernel
+ *   dtype FA_DTYPE_F32:                 d % 16 == 0, d <= 128 -> exact-fp32 kernel
+ *   lse: optional device pointer to B*Hq*Nq floats, or NULL (the reference's intended signature carried
+ *        L / M pointers: kernels/FlashAttention.cuh:21,36,50).
+ *   scale <= 0 selects 1/sqrt(d) (reference: tests/main.cu:27, check.py:19).
+ */
+int fa_fwd(const void* Q, const void* K, const void* V, void* O, float* lse,
+           int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype, float scale, int causal, void* stream);
+
+/* fa_fwd_strided: same, with explicit element strides {batch, head, row} per tensor (innermost stride 1).
+ * Replaces: the reference's intended strided signature (kernels/FlashAttention.cuh:23-25, commented).
+ * strides = {q_b,q_h,q_n, k_b,k_h,k_n, v_b,v_h,v_n, o_b,o_h,o_n}.  Enables check.py's [B,N,H*d] layout
+ * (reference: check.py:14-16) without a transpose.  For 16-bit dtypes strides must be multiples of 8.
+ */
+int fa_fwd_strided(const void* Q, const void* K, const void* V, void* O, float* lse,
+                   int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype, float scale, int causal,
+                   const long long* strides, void* stream);
+
+/* fa_mha_fwd_f32: the reference kernel's argument list as a C function; the template parameter D_HEAD becomes
+ * the runtime argument d_head (Q_TILE_ROWS / KV_TILE_ROWS are chosen by the library).
+ * Replaces: twoLoaderMhaFlashAttentionKernel<D_HEAD,QT,KVT>(Q,K,V,O,batchSize,numHeads,seqLen,scale,is_causal)
+ *           (reference: kernels/FlashAttention.cuh:59-63) for callers that do not want to pick a launch shape.
+ */
+int fa_mha_fwd_f32(const float* Q, const float* K, const float* V, float* O,
+                   int batchSize, int numHeads, int seqLen, int d_head, float scale, int is_causal, void* stream);
+
+/* fa_fwd_host: end-to-end call on HOST buffers (same layout as fa_fwd): H2D copies, kernel, D2H copy,
+ * pipelined over batch*head chunks on internal streams; synchronises before returning.
+ * Replaces: the cudaMalloc / cudaMemcpy H2D / launch / cudaDeviceSynchronize / cudaMemcpy D2H sequence of the
+ *           reference's driver (reference: tests/main.cu:39-66; main.cpp:30-33 is the intended home).
+ * Pinned host memory gives full PCIe bandwidth; pageable memory works but copies serialise.
+ */
+int fa_fwd_host(const void* hQ, const void* hK, const void* hV, void* hO, float* hlse,
+                int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype, float scale, int causal);
+
+/* ---- ring-KV building blocks (sequence-sharded long context) ---------------------------------
+ * fa_merge_partial: acc (fp32 O [rows,d], lse [rows]) <- combine(acc, partial (16-bit O, fp32 lse)) over
+ * disjoint key ranges.  Initialise acc_lse to -inf and acc_o to 0.  No reference counterpart (the reference
+ * has no multi-device code); the carry it implements is the (running_max, running_l) recurrence of
+ * reference utils.cuh:63-80 applied across ring steps instead of across tiles.
+ */
+int fa_merge_partial(float* acc_o, float* acc_lse, const void* part_o, const float* part_lse,
+                     long long rows, int d, int dtype, void* stream);
+/* fa_cast_out: fp32 accumulator -> 16-bit output tensor (n elements, n even). */
+int fa_cast_out(const float* src, void* dst, long long n, int dtype, void* stream);
+
+/* ---- host helpers (reference: helpers.hpp:8-36, main.cpp:5-26) ----------------------------------------------*/
+typedef struct {
+    int cc_major, cc_minor, sm_count;
+    size_t global_mem_bytes, smem_per_block_optin, smem_per_sm;
+    int regs_per_sm, warp_size, l2_bytes, max_threads_per_sm;
+} fa_device_info_t;
+/* Replaces check_gpu_props() (reference: main.cpp:5-26) — fills a struct instead of printing. */
+int fa_device_info(int device, fa_device_info_t* out);
+/* Replace calculateSizeBlockQ / calculateSizeBlockKV (reference: helpers.hpp:8-30): rows per CTA and per KV tile. */
+int fa_block_q(int d, int dtype);
+int fa_block_kv(int d, int dtype);
+/* Replaces getNumCta (reference: helpers.hpp:33-36): CTAs along the query axis; ragged sizes round up, no assert. */
+int fa_num_cta(int q_dim, int q_block_size);
+
+/* ---- diagnostics -------------------------------------------------------------------------------------------*/
+const char* fa_last_error(void);          /* thread-local text of the last failure, "" if none */
+long long fa_launch_count(void);          /* kernels this library has launched since load (bench: gpu_launches) */
+const char* fa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H_ */

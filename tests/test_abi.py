@@ -1,0 +1,85 @@
+"""CPU tests (-m "not gpu"): the C-ABI library builds for sm_100a, loads without a GPU, exports every symbol that
+include/fa_b200.h declares, and its host-only helpers behave like the reference's helpers.hpp contracts."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import fa_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    fa_b200.build()
+    return fa_b200.lib()
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "fa_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(fa_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported(L):
+    names = _declared()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/fa_b200.h but not exported"
+    assert sorted(fa_b200.EXPORTS) == names
+
+
+def test_library_is_sm100a_native():
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", fa_b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR"):
+        assert mnemonic in sass, f"{mnemonic} missing from SASS: the tcgen05/TMA path did not compile"
+    assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
+
+
+def test_host_helpers(L):
+    # getNumCta (helpers.hpp:33-36) without the divisibility assert: ragged sizes round up
+    assert L.fa_num_cta(8192, 256) == 32 and L.fa_num_cta(8193, 256) == 33 and L.fa_num_cta(0, 256) == 0
+    # calculateSizeBlockQ / KV (helpers.hpp:8-30): the sm_100a tile table
+    assert L.fa_block_q(128, fa_b200.FA_DTYPE_BF16) == 256 and L.fa_block_kv(128, fa_b200.FA_DTYPE_BF16) == 128
+    assert L.fa_block_q(64, fa_b200.FA_DTYPE_F32) == 64
+    assert b"sm_100a" in L.fa_version()
+
+
+def test_argument_validation_without_gpu(L):
+    # validation happens before any CUDA call, so it can be exercised on a CPU-only box
+    assert L.fa_fwd(None, None, None, None, None, 1, 1, 1, 16, 16, 64, 2, 0.0, 0, None) == -1
+    assert b"null" in L.fa_last_error()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert L.fa_fwd(p, p, p, p, None, 1, 3, 2, 16, 16, 64, 2, 0.0, 0, None) == -1     # Hq % Hkv != 0
+    assert L.fa_fwd(p, p, p, p, None, 1, 1, 1, 0, 16, 64, 2, 0.0, 0, None) == -1      # empty sequence
+    assert L.fa_fwd(p, p, p, p, None, 1, 1, 1, 16, 16, 64, 7, 0.0, 0, None) == -1     # unknown dtype
+    assert L.fa_merge_partial(None, None, None, None, 0, 0, 2, None) == -1
+    assert L.fa_launch_count() == 0                                                    # nothing was launched
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(fa_b200, "_lib", None)
+    monkeypatch.setattr(fa_b200, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(fa_b200.FaError):
+        fa_b200.lib()
+
+
+def test_no_cpu_fallback_for_cpu_tensors(L):
+    import torch
+    x = torch.zeros(1, 1, 16, 64, dtype=torch.bfloat16)
+    with pytest.raises(fa_b200.FaError):
+        fa_b200.attention_forward(x, x, x)
+
+
+def test_product_does_not_touch_oracle():
+    pkg = os.path.join(ROOT, "flash-attention-cuda-c_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h", ".sh")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.lower(), f"{f} mentions the oracle: the product path must not use it"
