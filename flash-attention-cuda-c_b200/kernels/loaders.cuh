@@ -129,6 +129,11 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
                                  hf * kHalfCols, j * kBlockN, w.h_kv, w.b, kEvictLast);
         }
     }
+    // Tail: wait until the consumer has handed back the last fills, so that no tcgen05.commit arrive is still in
+    // flight towards this CTA's shared memory when the CTA exits.
+    const int total = it;
+    for (int i = (total > STAGES ? total - STAGES : 0); i < total; ++i)
+        mbar_wait(bar0 + 8 * (L::kBarKVEmpty + i % STAGES), (i / STAGES) & 1);
 }
 
 }  // namespace fa

@@ -117,16 +117,20 @@ def test_config2_gpt2_shape_fp16():
 
 
 def test_check_py_layout_strided(golden_dir):
-    # check.py's (batch, seq, d_model) layout through fa_fwd_strided, against the reference's golden outputs
-    for f in sorted(glob.glob(os.path.join(golden_dir, "mh_*.npz"))):
-        g = np.load(f)
-        h = int(g["num_heads"])
-        Q, K, V = (torch.from_numpy(g[n]).to(torch.bfloat16) for n in ("Q", "K", "V"))
-        out = fa_b200.multi_head_attention(Q.cuda(), K.cuda(), V.cuda(), h).float().cpu()
-        ref, _ = oracle.multi_head_attention(Q.float(), K.float(), V.float(), h)
-        assert (out - ref).abs().max().item() <= TOL16
-        # and against the reference's own fp32 output on unrounded inputs (bf16 input rounding included)
-        assert (out.numpy() - g["output"]).max() <= 5e-2
+    # check.py's (batch, seq, d_model) layout through fa_fwd_strided, against the reference's golden outputs:
+    # head dim 128 on the bf16 tensor-core path, head dim 32 on the fp32 path
+    g = np.load(os.path.join(golden_dir, "mh_b1_n384_h2_d128.npz"))
+    h = int(g["num_heads"])
+    Q, K, V = (torch.from_numpy(g[n]).to(torch.bfloat16) for n in ("Q", "K", "V"))
+    out = fa_b200.multi_head_attention(Q.cuda(), K.cuda(), V.cuda(), h).float().cpu()
+    ref, _ = oracle.multi_head_attention(Q.float(), K.float(), V.float(), h)
+    assert (out - ref).abs().max().item() <= TOL16
+    # and against the reference's own fp32 output on unrounded inputs (bf16 input rounding included)
+    assert np.abs(out.numpy() - g["output"]).max() <= 5e-2
+    g = np.load(os.path.join(golden_dir, "mh_b2_n200_h4_d32.npz"))
+    Q, K, V = (torch.from_numpy(g[n]).cuda() for n in ("Q", "K", "V"))
+    out = fa_b200.multi_head_attention(Q, K, V, int(g["num_heads"])).cpu().numpy()
+    assert np.abs(out - g["output"]).max() / np.abs(g["output"]).max() <= RTOL32
 
 
 # ---- fp32 path ------------------------------------------------------------------------------------------
