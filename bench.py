@@ -36,7 +36,9 @@ WORKLOADS = {
     "cfg3nc": (8, 32, 32, 8192, 128, False, "bf16", "B=8 H=32 N=8192 d=128 non-causal bf16"),
     "cfg2": (4, 12, 12, 1024, 64, False, "fp16", "GPT-2 shape B=4 H=12 N=1024 d=64 non-causal fp16 (BASELINE configs[1])"),
     "cfg4": (16, 64, 8, 32768, 128, True, "bf16", "GQA Hq=64 Hkv=8 N=32K B=16 d=128 causal bf16 (BASELINE configs[3]); per GPU: B=16/N ranks"),
+    "cfg5": (1, 8, 8, 131072, 128, True, "bf16", "long context N=128K d=128 causal bf16, B=1 H=8, sequence-sharded ring-KV (BASELINE configs[4]); per GPU: N/ranks rows, zig-zag"),
 }
+STRONG = {"cfg4", "cfg5"}   # total work fixed as ranks grow; cfg2/cfg3 replicate the per-GPU workload (weak)
 METRIC = "attention fwd TFLOP/s (bf16, d=128, N=8K causal), whole job; roofline.frac = fraction of measured dense bf16 TC peak"
 
 
@@ -148,6 +150,11 @@ def run_ours(args, wl, wl_name):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if wl_name == "cfg4":
         B = max(1, B // world)   # 128 kv groups sharded by batch: strong-scaled config, 16/N batches per GPU
+    ring = wl_name == "cfg5"
+    N_total = N
+    if ring:
+        import sharding
+        N = N // world           # this rank's rows (two zig-zag chunks of N/(2*world))
     tdt = {"bf16": torch.bfloat16, "fp16": torch.float16}[dtype]
     dev = torch.device("cuda", local)
     g = torch.Generator(device=dev).manual_seed(rank)
@@ -156,6 +163,8 @@ def run_ours(args, wl, wl_name):
     v = torch.randn(B, Hkv, N, d, device=dev, generator=g).to(tdt)
     o = torch.empty_like(q)
     F = flops(B, Hq, N, N, d, causal)
+    if ring:
+        F = flops(B, Hq, N_total, N_total, d, causal) / world   # this rank's share of the whole-sequence work
     es = 2
     alg_bytes = (2 * B * Hq * N * d + 2 * B * Hkv * N * d) * es
     flush = None
@@ -163,7 +172,10 @@ def run_ours(args, wl, wl_name):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
-        fa_b200.attention_forward(q, k, v, causal=causal, out=o)
+        if ring:
+            sharding.ring_attention(q, k, v, causal=causal)
+        else:
+            fa_b200.attention_forward(q, k, v, causal=causal, out=o)
 
     def barrier():
         if dist is not None:
@@ -202,6 +214,8 @@ def run_ours(args, wl, wl_name):
     e2e = None
     e2e_steps = max(1, min(args.steps, 3))
     try:
+        if ring:
+            raise RuntimeError("ring-KV keeps Q/K/V sharded and resident on the GPUs; the host-buffer path is measured on cfg3")
         hq, hk, hv = (t.cpu().pin_memory() for t in (q, k, v))
         ho = torch.empty_like(hq).pin_memory()
         fa_b200.attention_forward_host(hq, hk, hv, ho, causal=causal)   # warm-up (allocates the staging buffers)
@@ -250,10 +264,11 @@ def run_ours(args, wl, wl_name):
                    "kind": "port", "seconds": dt,
                    "sample": f"{heads} of {B * Hq} (batch, head) slices, fp32, torch-CPU port of check.py:4-25 (scores materialised)"}
         line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if wl_name in STRONG else "weak", "vs_baseline": None,
                 "dtype": dtype, "data": "synthetic",
                 "config": {"workload": desc, "per_gpu": {"B": B, "Hq": Hq, "Hkv": Hkv, "N": N, "d": d, "causal": causal},
-                           "sharding": "(batch x head) units per rank, no data-path collective",
+                           "sharding": ("sequence-sharded ring-KV: K/V blocks rotate with NCCL send/recv, one hop per step, overlapped with the MMAs"
+                                        if ring else "(batch x head) units per rank, no data-path collective"),
                            "l2": ("working set %.2f GiB > 126 MB L2" % (alg_bytes / 2**30)) if flush is None else "L2 flushed (256 MiB write) between timed iterations",
                            "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -1,0 +1,169 @@
+// main.cpp — host driver of the attention forward path (verify + bench), C++ over the C ABI.
+//
+// The reference's main.cpp defines check_gpu_props() and an empty main() (reference: main.cpp:5-33); the
+// intended flow (helpers.hpp:8-36 + the archived grid mapping) was: query device -> pick tile sizes -> launch.
+// This driver is that flow on B200: it prints the device properties and the tile table, fills Q/K/V with seeded
+// random data, shards the (batch, kv-head) units over G GPUs (one host thread and one stream per GPU, no
+// communication), runs fa_fwd, verifies a sample of rows against a plain host loop and reports TFLOP/s as the
+// max over GPUs.  Build: see run.sh.
+//
+//   ./fa_main [--B 8] [--H 32] [--Hkv 32] [--N 8192] [--d 128] [--dtype bf16|fp16|fp32] [--causal 1]
+//             [--iters 20] [--gpus 1] [--verify 1] [--props]
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "helpers.hpp"
+
+// same name as the reference (main.cpp:5-26); data comes from fa_device_info instead of ad-hoc queries
+void check_gpu_props(int device = 0) {
+    fa_device_info_t p;
+    if (fa_device_info(device, &p) != FA_OK) { printf("device %d: %s\n", device, fa_last_error()); return; }
+    printf("Compute capability: %d.%d\n", p.cc_major, p.cc_minor);
+    printf("Multiprocessor count: %d\n", p.sm_count);
+    printf("Global memory: %zu MB\n", p.global_mem_bytes / (1024 * 1024));
+    printf("Shared memory per block (opt-in): %zu KB\n", p.smem_per_block_optin / 1024);
+    printf("Shared memory per SM: %zu KB\n", p.smem_per_sm / 1024);
+    printf("Registers per SM: %d\n", p.regs_per_sm);
+    printf("Warp size: %d\n", p.warp_size);
+    printf("L2 cache size: %d KB\n", p.l2_bytes / 1024);
+    printf("Max threads per SM: %d\n", p.max_threads_per_sm);
+}
+
+namespace {
+
+uint16_t to16(float f, int dtype) {   // round-to-nearest-even fp32 -> bf16 / fp16 bits
+    uint32_t u; memcpy(&u, &f, 4);
+    if (dtype == FA_DTYPE_BF16) { u += 0x7fffu + ((u >> 16) & 1u); return uint16_t(u >> 16); }
+    const uint32_t sign = (u >> 16) & 0x8000u; int32_t e = int32_t((u >> 23) & 0xff) - 127 + 15; uint32_t m = u & 0x7fffffu;
+    if (e >= 31) return uint16_t(sign | 0x7c00u);
+    if (e <= 0) { if (e < -10) return uint16_t(sign); m |= 0x800000u; const int sh = 14 - e; uint32_t h = m >> sh; const uint32_t rem = m & ((1u << sh) - 1), half = 1u << (sh - 1);
+                  if (rem > half || (rem == half && (h & 1))) ++h; return uint16_t(sign | h); }
+    uint32_t h = (uint32_t(e) << 10) | (m >> 13); const uint32_t rem = m & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;
+    return uint16_t(sign | h);
+}
+float from16(uint16_t h, int dtype) {
+    uint32_t u;
+    if (dtype == FA_DTYPE_BF16) { u = uint32_t(h) << 16; }
+    else { const uint32_t s = (h & 0x8000u) << 16; uint32_t e = (h >> 10) & 0x1f, m = h & 0x3ffu;
+           if (e == 0) { if (m == 0) u = s; else { e = 1; while (!(m & 0x400u)) { m <<= 1; --e; } m &= 0x3ffu; u = s | ((e + 112) << 23) | (m << 13); } }
+           else if (e == 31) u = s | 0x7f800000u | (m << 13); else u = s | ((e + 112) << 23) | (m << 13); }
+    float f; memcpy(&f, &u, 4); return f;
+}
+
+struct Opt { int B = 8, H = 32, Hkv = 32, N = 8192, d = 128, dtype = FA_DTYPE_BF16, causal = 1, iters = 20, gpus = 1, verify = 1; bool props = false; };
+
+struct Shard { int dev; long long unit0, units; double ms = 0; double max_err = 0; int rc = 0; std::string err; };
+
+// host attention for one query row (plain loop; scale 1/sqrt(d), causal rule j <= i)
+void host_row(const std::vector<float>& q, const std::vector<float>& k, const std::vector<float>& v, int N, int d, int i, bool causal,
+              std::vector<double>& out) {
+    const int nk = causal ? i + 1 : N; std::vector<double> p(nk); double mx = -1e300, sum = 0;
+    for (int j = 0; j < nk; ++j) { double s = 0; for (int c = 0; c < d; ++c) s += double(q[size_t(i) * d + c]) * k[size_t(j) * d + c]; p[j] = s / std::sqrt(double(d)); mx = std::max(mx, p[j]); }
+    for (int j = 0; j < nk; ++j) { p[j] = std::exp(p[j] - mx); sum += p[j]; }
+    out.assign(d, 0.0);
+    for (int j = 0; j < nk; ++j) for (int c = 0; c < d; ++c) out[c] += p[j] * v[size_t(j) * d + c];
+    for (int c = 0; c < d; ++c) out[c] /= sum;
+}
+
+void run_shard(const Opt& o, Shard& s) {
+    auto fail = [&](const char* what) { s.rc = 1; s.err = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError()) + " / " + fa_last_error(); };
+    if (cudaSetDevice(s.dev) != cudaSuccess) return fail("cudaSetDevice");
+    const int g = o.H / o.Hkv; const size_t es = o.dtype == FA_DTYPE_F32 ? 4 : 2;
+    const size_t q_unit = size_t(g) * o.N * o.d, kv_unit = size_t(o.N) * o.d;
+    // one unit = one (batch, kv head): g query heads sharing one K/V head; a shard is a contiguous run of units
+    std::vector<float> hq(q_unit), hk(kv_unit), hv(kv_unit);
+    std::mt19937 rng(1234u + unsigned(s.unit0)); std::normal_distribution<float> nd(0.f, 1.f);
+    for (auto& x : hq) x = nd(rng); for (auto& x : hk) x = nd(rng); for (auto& x : hv) x = nd(rng);
+    std::vector<uint8_t> bq(q_unit * es), bk(kv_unit * es), bv(kv_unit * es);
+    auto pack = [&](std::vector<float>& src, std::vector<uint8_t>& dst) {
+        for (size_t i = 0; i < src.size(); ++i) {
+            if (es == 4) memcpy(&dst[i * 4], &src[i], 4);
+            else { const uint16_t h = to16(src[i], o.dtype); memcpy(&dst[i * 2], &h, 2); src[i] = from16(h, o.dtype); }
+        }
+    };
+    pack(hq, bq); pack(hk, bk); pack(hv, bv);
+    void *dq, *dk, *dv, *dO;
+    if (cudaMalloc(&dq, s.units * q_unit * es) || cudaMalloc(&dk, s.units * kv_unit * es) || cudaMalloc(&dv, s.units * kv_unit * es) ||
+        cudaMalloc(&dO, s.units * q_unit * es)) return fail("cudaMalloc");
+    cudaStream_t st; cudaStreamCreate(&st);
+    for (long long u = 0; u < s.units; ++u) {   // every unit of the shard gets the same seeded data (unit 0 is the one verified)
+        cudaMemcpyAsync((char*)dq + u * q_unit * es, bq.data(), q_unit * es, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync((char*)dk + u * kv_unit * es, bk.data(), kv_unit * es, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync((char*)dv + u * kv_unit * es, bv.data(), kv_unit * es, cudaMemcpyHostToDevice, st);
+    }
+    auto launch = [&] { return fa_fwd(dq, dk, dv, dO, nullptr, int(s.units), g, 1, o.N, o.N, o.d, o.dtype, 0.f, o.causal, st); };
+    for (int i = 0; i < 3; ++i) if (launch() != FA_OK) return fail("fa_fwd");
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaStreamSynchronize(st);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < o.iters; ++i) if (launch() != FA_OK) return fail("fa_fwd");
+    cudaEventRecord(e1, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail("sync");
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); s.ms = ms / o.iters;
+    if (o.verify) {
+        std::vector<uint8_t> bo(q_unit * es);
+        cudaMemcpy(bo.data(), dO, q_unit * es, cudaMemcpyDeviceToHost);
+        std::vector<double> ref;
+        const int rows[] = {0, 1, o.N / 3, o.N / 2 + 7, o.N - 1};
+        for (int r : rows) {
+            if (r < 0 || r >= o.N) continue;
+            host_row(hq, hk, hv, o.N, o.d, r, o.causal != 0, ref);   // query head 0 of the unit
+            for (int c = 0; c < o.d; ++c) {
+                float got; if (es == 4) memcpy(&got, &bo[(size_t(r) * o.d + c) * 4], 4); else { uint16_t h; memcpy(&h, &bo[(size_t(r) * o.d + c) * 2], 2); got = from16(h, o.dtype); }
+                s.max_err = std::max(s.max_err, std::fabs(double(got) - ref[c]));
+            }
+        }
+    }
+    cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dO); cudaStreamDestroy(st);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Opt o;
+    for (int i = 1; i < argc; ++i) {
+        auto val = [&](int& dst) { if (i + 1 < argc) dst = atoi(argv[++i]); };
+        if (!strcmp(argv[i], "--B")) val(o.B); else if (!strcmp(argv[i], "--H")) val(o.H); else if (!strcmp(argv[i], "--Hkv")) val(o.Hkv);
+        else if (!strcmp(argv[i], "--N")) val(o.N); else if (!strcmp(argv[i], "--d")) val(o.d); else if (!strcmp(argv[i], "--causal")) val(o.causal);
+        else if (!strcmp(argv[i], "--iters")) val(o.iters); else if (!strcmp(argv[i], "--gpus")) val(o.gpus); else if (!strcmp(argv[i], "--verify")) val(o.verify);
+        else if (!strcmp(argv[i], "--props")) o.props = true;
+        else if (!strcmp(argv[i], "--dtype") && i + 1 < argc) { ++i; o.dtype = !strcmp(argv[i], "fp32") ? FA_DTYPE_F32 : !strcmp(argv[i], "fp16") ? FA_DTYPE_F16 : FA_DTYPE_BF16; }
+        else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
+    }
+    if (o.H % o.Hkv) { fprintf(stderr, "H must be a multiple of Hkv\n"); return 2; }
+    int ndev = 0; cudaGetDeviceCount(&ndev);
+    if (ndev == 0) { fprintf(stderr, "no CUDA device: this driver has no CPU path\n"); return 3; }
+    o.gpus = std::max(1, std::min(o.gpus, ndev));
+    if (o.props) check_gpu_props(0);
+    cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
+    const int bq = o.dtype == FA_DTYPE_F32 ? calculateSizeBlockQ(o.d, o.dtype) : calculateSizeBlockQ(prop, o.d);
+    const int bkv = o.dtype == FA_DTYPE_F32 ? calculateSizeBlockKV(o.d, o.dtype) : calculateSizeBlockKV(prop, o.d, 0);
+    printf("%s | tiles: %d query rows / CTA, %d kv rows / stage, %d CTAs per (batch, head)\n", fa_version(), bq, bkv, getNumCta(o.N, bq));
+
+    // (batch, kv-head) units -> contiguous slices, one per GPU, no communication
+    const long long units = (long long)o.B * o.Hkv;
+    std::vector<Shard> shards(o.gpus);
+    for (int r = 0; r < o.gpus; ++r) { shards[r].dev = r; shards[r].unit0 = units * r / o.gpus; shards[r].units = units * (r + 1) / o.gpus - shards[r].unit0; }
+    std::vector<std::thread> th;
+    for (auto& s : shards) if (s.units > 0) th.emplace_back(run_shard, std::cref(o), std::ref(s));
+    for (auto& t : th) t.join();
+    double ms = 0, err = 0; int rc = 0;
+    for (auto& s : shards) { ms = std::max(ms, s.ms); err = std::max(err, s.max_err); if (s.rc) { rc = 1; fprintf(stderr, "gpu %d: %s\n", s.dev, s.err.c_str()); } }
+    if (rc) return 1;
+    const double flops = 4.0 * o.B * o.H * double(o.N) * o.N * o.d * (o.causal ? 0.5 : 1.0);
+    const double tol = o.dtype == FA_DTYPE_F32 ? 1e-4 : 2e-2;
+    printf("{\"B\": %d, \"H\": %d, \"Hkv\": %d, \"N\": %d, \"d\": %d, \"dtype\": %d, \"causal\": %d, \"gpus\": %d, \"ms\": %.4f, \"tflops\": %.1f, \"max_abs_err\": %.3e, \"verified\": %s}\n",
+           o.B, o.H, o.Hkv, o.N, o.d, o.dtype, o.causal, o.gpus, ms, flops / ms / 1e9, err, o.verify ? (err <= tol ? "true" : "false") : "null");
+    return (o.verify && err > tol) ? 1 : 0;
+}

@@ -1,0 +1,152 @@
+"""sharding.py — the two multi-GPU modes of the attention forward path.  The reference has no
+multi-device code at all; both modes are built on the single-GPU kernel behind the C ABI.
+
+1. (batch x kv-head) sharding — no communication.  `shard_units` gives rank r a contiguous slice of the
+   B*Hkv independent units (each unit carries its Hq/Hkv query heads, so K/V are never duplicated).
+
+2. ring-KV — sequence-sharded long context.  Q/O stay resident on their rank; the K/V block of every rank
+   travels once around the ring with point-to-point send/recv (NCCL over NVLink on GPUs; gloo in the CPU tests),
+   posted before the local attention call so the transfer overlaps the MMAs.  Partial results over disjoint key
+   ranges are folded with the (O, log-sum-exp) carry of fa_merge_partial — the reference's running
+   (max, sum) recurrence (reference: kernels/utils.cuh:63-80) applied across ring steps instead of across tiles.
+   Causal work is balanced with the zig-zag layout: the sequence is cut into 2P chunks and rank r owns chunks
+   r and 2P-1-r, so every rank does the same amount of unmasked work at every step and fully masked block pairs
+   are never launched.
+
+The ring driver takes the local attention and merge operators as arguments: on GPUs they default to the CUDA
+path (fa_b200); the CPU tests (gloo, world_size 2) pass oracle-backed stand-ins to check schedule and plumbing.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+
+def shard_units(B: int, Hkv: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous slice [u0, u0+n) of the B*Hkv (batch, kv-head) units owned by `rank`."""
+    units = B * Hkv
+    u0 = units * rank // world
+    u1 = units * (rank + 1) // world
+    return u0, u1 - u0
+
+
+def zigzag_chunks(world: int, rank: int) -> Tuple[int, int]:
+    """Indices (of 2*world sequence chunks) owned by `rank` in the causal zig-zag layout."""
+    return rank, 2 * world - 1 - rank
+
+
+def zigzag_split(x, world: int, rank: int, dim: int = 2):
+    """Take this rank's two chunks of a full-sequence tensor (test / setup helper)."""
+    import torch
+    chunks = x.chunk(2 * world, dim=dim)
+    a, b = zigzag_chunks(world, rank)
+    return torch.cat([chunks[a], chunks[b]], dim=dim).contiguous()
+
+
+def zigzag_merge(parts, world: int, dim: int = 2):
+    """Inverse of zigzag_split over the list of per-rank tensors (test helper)."""
+    import torch
+    chunks = [None] * (2 * world)
+    for r, p in enumerate(parts):
+        a, b = p.chunk(2, dim=dim)
+        ia, ib = zigzag_chunks(world, r)
+        chunks[ia], chunks[ib] = a, b
+    return torch.cat(chunks, dim=dim)
+
+
+def ring_schedule(world: int, rank: int, causal: bool):
+    """The list of local attention calls of one rank, per ring step.  Each entry is
+    (step, src_rank, q_part, kv_part, causal_flag) with parts in {'a','b','ab'} ('a'/'b' = first / second local
+    chunk, 'ab' = both).  Fully masked block pairs do not appear."""
+    out = []
+    for s in range(world):
+        src = (rank - s) % world
+        if not causal:
+            out.append((s, src, "ab", "ab", False))
+        elif s == 0:
+            out.append((s, src, "a", "a", True))     # diagonal block of the early chunk
+            out.append((s, src, "b", "ab", True))    # late chunk: all of Ka, causal inside Kb (bottom-right aligned)
+        elif src < rank:
+            out.append((s, src, "a", "a", False))    # only the sender's early chunk is visible, to both local chunks
+            out.append((s, src, "b", "a", False))
+        else:
+            out.append((s, src, "b", "ab", False))   # only the local late chunk sees the sender's (both) chunks
+    return out
+
+
+def _default_ops():
+    import torch
+    import fa_b200
+
+    def attn(q, k, v, causal):
+        return fa_b200.attention_forward(q, k, v, causal=causal, return_lse=True)
+
+    def merge(acc_o, acc_lse, o, lse):
+        fa_b200.merge_partial(acc_o, acc_lse, o, lse)
+
+    def finish(acc, like):
+        return fa_b200.cast_out(acc, torch.empty(acc.shape, dtype=like.dtype, device=acc.device))
+
+    return attn, merge, finish
+
+
+def ring_attention(q, k, v, causal: bool = True, group=None,
+                   attn_fn: Optional[Callable] = None, merge_fn: Optional[Callable] = None,
+                   finish_fn: Optional[Callable] = None, return_lse: bool = False):
+    """Sequence-sharded attention.  q [B,Hq,n,d], k/v [B,Hkv,n,d] are this rank's shard of the sequence
+    (zig-zag layout when causal: [chunk r ; chunk 2P-1-r], contiguous otherwise).  Returns this rank's shard of O.
+    One send + one recv of the packed K/V block per step, none on the last step."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0   # degenerate ring: one rank owns the whole sequence, no communication
+    if attn_fn is None or merge_fn is None or finish_fn is None:
+        d_attn, d_merge, d_finish = _default_ops()
+        attn_fn, merge_fn, finish_fn = attn_fn or d_attn, merge_fn or d_merge, finish_fn or d_finish
+
+    B, Hq, n, d = q.shape
+    half = n // 2
+    if causal and n % 2:
+        raise ValueError("causal ring needs an even local length (two zig-zag chunks)")
+    # K and V travel as one buffer: a single send/recv pair per hop
+    kv = torch.stack([k, v]).contiguous()
+    nxt = torch.empty_like(kv) if world > 1 else None
+
+    def part(t, which):          # rows of the local sequence axis (dim -2); slices stay strided views
+        if which == "ab":
+            return t
+        return t[..., :half, :] if which == "a" else t[..., half:, :]
+
+    f32 = dict(device=q.device, dtype=torch.float32)
+    if causal:
+        acc = {"a": (torch.zeros(B, Hq, half, d, **f32), torch.full((B, Hq, half), float("-inf"), **f32)),
+               "b": (torch.zeros(B, Hq, n - half, d, **f32), torch.full((B, Hq, n - half), float("-inf"), **f32))}
+        qparts = {"a": part(q, "a").contiguous(), "b": part(q, "b").contiguous()}
+    else:
+        acc = {"ab": (torch.zeros(B, Hq, n, d, **f32), torch.full((B, Hq, n), float("-inf"), **f32))}
+        qparts = {"ab": q}
+
+    sched = ring_schedule(world, rank, causal)
+    send_to, recv_from = (rank + 1) % world, (rank - 1) % world
+    if group is not None:
+        send_to, recv_from = dist.get_global_rank(group, send_to), dist.get_global_rank(group, recv_from)
+    for s in range(world):
+        reqs = []
+        if s + 1 < world:   # post the hop for the NEXT step first: it overlaps the attention calls below
+            ops = [dist.P2POp(dist.isend, kv, send_to, group), dist.P2POp(dist.irecv, nxt, recv_from, group)]
+            reqs = dist.batch_isend_irecv(ops)
+        for (_, _, qp, kp, c) in [e for e in sched if e[0] == s]:
+            o, lse = attn_fn(qparts[qp], part(kv[0], kp), part(kv[1], kp), c)
+            merge_fn(acc[qp][0], acc[qp][1], o, lse)
+        for r in reqs:
+            r.wait()
+        if s + 1 < world:
+            kv, nxt = nxt, kv
+    if causal:
+        o = torch.cat([finish_fn(acc["a"][0], q), finish_fn(acc["b"][0], q)], dim=2)
+        lse = torch.cat([acc["a"][1], acc["b"][1]], dim=2)
+    else:
+        o, lse = finish_fn(acc["ab"][0], q), acc["ab"][1]
+    return (o, lse) if return_lse else o
