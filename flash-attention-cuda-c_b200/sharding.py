@@ -14,7 +14,7 @@ multi-device code at all; both modes are built on the single-GPU kernel behind t
    are never launched.
 
 The ring driver takes the local attention and merge operators as arguments: on GPUs they default to the CUDA
-path (fa_b200); the CPU tests (gloo, world_size 2) pass oracle-backed stand-ins to check schedule and plumbing.
+path (fa_b200); the CPU tests (gloo, world_size 2) pass CPU stand-ins to check schedule and plumbing.
 """
 from __future__ import annotations
 
