@@ -19,6 +19,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+unsigned long long* g_prof = nullptr;   // device buffer of phase counters; only set by fa_debug_set_profile_buffer
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -194,6 +195,7 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     p.o_stride_b = s[9]; p.o_stride_h = s[10]; p.o_stride_n = s[11];
     p.scale = sc; p.scale_log2 = sc * 1.4426950408889634f;
     p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
+    p.prof = g_prof;
 
     if (d == 128) {
         return dtype == FA_DTYPE_BF16 ? launch_sm100<128, 5, fa::kBF16>(tq, tk, tv, p, st)
@@ -217,6 +219,9 @@ HostPipe g_pipe;
 }  // namespace
 
 extern "C" {
+
+// Debug hook (not in include/fa_b200.h): phase-counter buffer for FA_PHASE_PROFILE builds, 16 x u64 on the device.
+void fa_debug_set_profile_buffer(void* dev_ptr) { g_prof = (unsigned long long*)dev_ptr; }
 
 const char* fa_last_error(void) { return g_err; }
 long long fa_launch_count(void) { return g_launches.load(); }

@@ -33,7 +33,8 @@ constexpr float kRescaleThreshold = 8.0f;   // log2 units
 // Issue order per key tile j (t = query tile):  P_0V_j, Q_0K_{j+1}, P_1V_j, Q_1K_{j+1}
 // ------------------------------------------------------------------------------------------------
 template <int D, int STAGES, int DT>
-__device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tmem_base, const WorkItem& w) {
+__device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tmem_base, const WorkItem& w,
+                                                unsigned long long* prof = nullptr) {
     using L = SmemLayout<D, STAGES>;
     constexpr uint32_t kFmt = (DT == kBF16) ? 1u : 0u;
     constexpr uint32_t idesc_qk = umma_idesc(kBlockM, kBlockN, kFmt, 0, 0);
@@ -71,9 +72,11 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
     auto wait_full = [&](int it) { mbar_wait(bar(L::kBarKVFull + it % STAGES), (it / STAGES) & 1); };
     auto release = [&](int it) { tc_commit(bar(L::kBarKVEmpty + it % STAGES)); };
 
+    FA_PROF_DECL(4);
     mbar_wait(bar(L::kBarQFull), 0);
     wait_full(0);
     tc_fence_after();
+    FA_PROF_MARK(0);                 // prologue: Q + K0 arrival
     issue_qk(0, slot_addr(0));
     tc_commit(bar(L::kBarSFull + 0));
     issue_qk(1, slot_addr(0));
@@ -83,17 +86,22 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
     for (int j = 0; j < w.n_kv; ++j) {
         const int it_v = 2 * j + 1, it_k = 2 * j + 2;
         const bool has_next = j + 1 < w.n_kv;
+        FA_PROF_MARK(3);             // issue + bookkeeping
         wait_full(it_v);
+        FA_PROF_MARK(1);             // waiting for V/K tiles
 #pragma unroll
         for (int t = 0; t < kTilesPerCta; ++t) {
             mbar_wait(bar(L::kBarPFull + t), j & 1);
             tc_fence_after();
+            FA_PROF_MARK(2);         // waiting for P
             issue_pv(t, slot_addr(it_v), j > 0);
             tc_commit(bar(L::kBarOFull + t));
             if (has_next) {
                 if (t == 0) {
+                    FA_PROF_MARK(3);
                     wait_full(it_k);
                     tc_fence_after();
+                    FA_PROF_MARK(1);
                 }
                 issue_qk(t, slot_addr(it_k));
                 tc_commit(bar(L::kBarSFull + t));
@@ -102,6 +110,8 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
         release(it_v);
         if (has_next) release(it_k);
     }
+    FA_PROF_MARK(3);
+    FA_PROF_FLUSH(prof, 8, 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -130,14 +140,18 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
     float m_run = -INFINITY;   // max in use, in raw (unscaled) score units
     float l_run = 0.f;
 
+    FA_PROF_DECL(6);
     for (int j = 0; j < w.n_kv; ++j) {
+        FA_PROF_MARK(5);             // loop overhead / l update
         mbar_wait(s_full, j & 1);
         tc_fence_after();
+        FA_PROF_MARK(0);             // waiting for S
 
         uint32_t r[kBlockN];
 #pragma unroll
         for (int q = 0; q < kBlockN / 32; ++q) tmem_ld32(tS + 32u * q, r + 32 * q);
         tc_wait_ld();
+        FA_PROF_MARK(1);             // tcgen05.ld of the score row
 
         const int kv0 = j * kBlockN;
         const bool need_mask = (kv0 + kBlockN > p.Nk) || (p.causal && (kv0 + kBlockN - 1 > tile_row0 + p.causal_off));
@@ -180,6 +194,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 if (grow) m_run = m_new;
             }
         }
+        FA_PROF_MARK(2);             // mask + row max + (rare) O rescale
         const float m_safe = (m_run == -INFINITY) ? 0.f : m_run;
         const float2 c2 = make_float2(c, c);
         const float2 nm2 = make_float2(-m_safe * c, -m_safe * c);
@@ -205,12 +220,15 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             }
             tmem_st32(tS + 32u * hf, pk);
         }
+        FA_PROF_MARK(3);             // exp2 / pack / tcgen05.st issue
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(p_full);
+        FA_PROF_MARK(4);             // store drain + arrive
 
         l_run += (s0.x + s0.y) + (s1.x + s1.y);
     }
+    if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 0, 6);
 
     // ---- epilogue: O / l -> global ----
     const bool row_ok = row < p.Nq;

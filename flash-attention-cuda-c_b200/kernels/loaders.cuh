@@ -46,6 +46,7 @@ struct FwdParams {
     int causal;              // 0/1
     int causal_off;          // Nk - Nq: key j visible to query i iff j <= i + causal_off
     int q_heads_per_kv;      // Hq / Hkv
+    unsigned long long* prof; // FA_PHASE_PROFILE builds only: per-phase cycle counters (see scripts/phase_profile.py)
 };
 
 template <int D, int STAGES>

@@ -25,6 +25,17 @@
 #define FA_HANG_GUARD_CYCLES (4000000000LL)
 #endif
 
+// Phase profiling (debug builds with -DFA_PHASE_PROFILE): cycle counters per pipeline phase, summed with atomics.
+#ifdef FA_PHASE_PROFILE
+#define FA_PROF_DECL(n) long long prof_acc_[n] = {}; long long prof_t_ = clock64()
+#define FA_PROF_MARK(i) do { const long long t_ = clock64(); prof_acc_[i] += t_ - prof_t_; prof_t_ = t_; } while (0)
+#define FA_PROF_FLUSH(ptr, base, n) do { if (ptr) for (int i_ = 0; i_ < (n); ++i_) atomicAdd((ptr) + (base) + i_, (unsigned long long)prof_acc_[i_]); } while (0)
+#else
+#define FA_PROF_DECL(n)
+#define FA_PROF_MARK(i)
+#define FA_PROF_FLUSH(ptr, base, n)
+#endif
+
 namespace fa {
 
 enum DType : int { kF32 = 0, kF16 = 1, kBF16 = 2 };
