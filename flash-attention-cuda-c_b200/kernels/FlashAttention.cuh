@@ -56,7 +56,8 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar0 + 8 * (L::kBarSFull + t), 1);
-            mbar_init(bar0 + 8 * (L::kBarPFull + t), 128);
+            mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t), 128);
+            mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t + 1), 128);
             mbar_init(bar0 + 8 * (L::kBarOFull + t), 1);
         }
         fence_mbar_init();

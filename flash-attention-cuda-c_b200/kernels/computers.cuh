@@ -58,12 +58,15 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
             umma_ss(d_tmem, a0 + off, b0 + off, idesc_qk, ks > 0);
         }
     };
-    auto issue_pv = [&](int t, uint32_t v_smem, bool accumulate) {
+    // P_t V_j in two halves of 4 k-steps (64 keys each): the first half can start while the softmax warpgroup is still
+    // producing the second half of P.
+    auto issue_pv_half = [&](int t, uint32_t v_smem, bool accumulate, int half) {
         const uint32_t p_tmem = tmem_base + kTmemS0 + 128u * t;    // P aliases the head of S_t
         const uint32_t d_tmem = tmem_base + kTmemO0 + 128u * t;
         const uint64_t b0 = desc_mn_major + (v_smem >> 4);
 #pragma unroll
-        for (int ks = 0; ks < kBlockN / 16; ++ks) {
+        for (int kk = 0; kk < kBlockN / 32; ++kk) {
+            const int ks = half * (kBlockN / 32) + kk;
             // 16 key rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B
             umma_ts(d_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (accumulate || ks > 0) ? 1u : 0u);
         }
@@ -91,10 +94,15 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
         FA_PROF_MARK(1);             // waiting for V/K tiles
 #pragma unroll
         for (int t = 0; t < kTilesPerCta; ++t) {
-            mbar_wait(bar(L::kBarPFull + t), j & 1);
+            mbar_wait(bar(L::kBarPFull + 2 * t), j & 1);
             tc_fence_after();
             FA_PROF_MARK(2);         // waiting for P
-            issue_pv(t, slot_addr(it_v), j > 0);
+            issue_pv_half(t, slot_addr(it_v), j > 0, 0);
+            FA_PROF_MARK(3);
+            mbar_wait(bar(L::kBarPFull + 2 * t + 1), j & 1);
+            tc_fence_after();
+            FA_PROF_MARK(2);
+            issue_pv_half(t, slot_addr(it_v), j > 0, 1);
             tc_commit(bar(L::kBarOFull + t));
             if (has_next) {
                 if (t == 0) {
@@ -124,7 +132,8 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
     using L = SmemLayout<D, STAGES>;
     const uint32_t bar0 = smem_base + L::kBarOff;
     const uint32_t s_full = bar0 + 8u * (L::kBarSFull + t);
-    const uint32_t p_full = bar0 + 8u * (L::kBarPFull + t);
+    const uint32_t p_full0 = bar0 + 8u * (L::kBarPFull + 2 * t);
+    const uint32_t p_full1 = p_full0 + 8u;
     const uint32_t o_full = bar0 + 8u * (L::kBarOFull + t);
 
     const int warp_in_wg = (threadIdx.x / 32) & 3;
@@ -200,30 +209,47 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
         const float2 nm2 = make_float2(-m_safe * c, -m_safe * c);
 
         float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-        // two halves of 64 scores -> 32 packed columns each; storing the first half early frees its registers
+        // exp2 of one score pair: MUFU.EX2 for most pairs, FMA-pipe emulation for kEmuPairsPer8 of every 8
+        auto exp_pair = [&](int col) -> float2 {
+            float2 x = fma2(make_float2(__uint_as_float(r[col]), __uint_as_float(r[col + 1])), c2, nm2);
+            if (((col / 2) % 8) * 3 % 8 < kEmuPairsPer8) {     // spread the emulated pairs evenly over the group of 8
+                x = ex2_emu2(x);
+            } else {
+                x.x = ex2_approx(x.x);
+                x.y = ex2_approx(x.y);
+            }
+            return x;
+        };
+        // 32 scores -> 16 packed columns
+        auto exp_quarter = [&](int qt, uint32_t* pk) {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            uint32_t pk[32];
-#pragma unroll
-            for (int cc = 0; cc < 64; cc += 4) {
-                const int b = 64 * hf + cc;
-                float2 x0 = fma2(make_float2(__uint_as_float(r[b + 0]), __uint_as_float(r[b + 1])), c2, nm2);
-                float2 x1 = fma2(make_float2(__uint_as_float(r[b + 2]), __uint_as_float(r[b + 3])), c2, nm2);
-                x0.x = ex2_approx(x0.x);
-                x0.y = ex2_approx(x0.y);
-                x1.x = ex2_approx(x1.x);
-                x1.y = ex2_approx(x1.y);
+            for (int cc = 0; cc < 32; cc += 4) {
+                const float2 x0 = exp_pair(32 * qt + cc), x1 = exp_pair(32 * qt + cc + 2);
                 s0 = add2(s0, x0);
                 s1 = add2(s1, x1);
                 pk[cc / 2 + 0] = pack16<DT>(x0.x, x0.y);
                 pk[cc / 2 + 1] = pack16<DT>(x1.x, x1.y);
             }
-            tmem_st32(tS + 32u * hf, pk);
+        };
+        {
+            uint32_t pk[32];
+            exp_quarter(0, pk);
+            exp_quarter(1, pk + 16);
+            tmem_st32(tS, pk);                 // keys 0..63 of P
+        }
+        {
+            uint32_t pk[32];
+            exp_quarter(2, pk);
+            tc_wait_st();                      // first half landed while quarter 2 was computed
+            tc_fence_before();
+            mbar_arrive(p_full0);              // MMA may start P V on keys 0..63
+            exp_quarter(3, pk + 16);
+            tmem_st32(tS + 32u, pk);           // keys 64..127 of P
         }
         FA_PROF_MARK(3);             // exp2 / pack / tcgen05.st issue
         tc_wait_st();
         tc_fence_before();
-        mbar_arrive(p_full);
+        mbar_arrive(p_full1);
         FA_PROF_MARK(4);             // store drain + arrive
 
         l_run += (s0.x + s0.y) + (s1.x + s1.y);

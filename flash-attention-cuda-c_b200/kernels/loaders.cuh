@@ -35,6 +35,11 @@ constexpr int kNumThreads = 384;
 // Register split (setmaxnreg): 384 x 168 at launch -> 256 x 208 (softmax) + 128 x 88 (MMA / TMA / TMEM warps)
 constexpr int kSoftmaxRegs = 208;
 constexpr int kOtherRegs = 88;
+// Of every 8 consecutive score pairs, this many take the FMA-pipe exp2 (ex2_emu2) instead of MUFU.EX2.
+#ifndef FA_EMU_PAIRS_PER_8
+#define FA_EMU_PAIRS_PER_8 3
+#endif
+constexpr int kEmuPairsPer8 = FA_EMU_PAIRS_PER_8;
 
 struct FwdParams {
     void* O;                 // output, same dtype as Q
@@ -61,8 +66,8 @@ struct SmemLayout {
     static constexpr int kBarKVFull = 1;
     static constexpr int kBarKVEmpty = kBarKVFull + STAGES;
     static constexpr int kBarSFull = kBarKVEmpty + STAGES;     // [2]  MMA -> softmax : S tile ready in TMEM
-    static constexpr int kBarPFull = kBarSFull + 2;            // [2]  softmax -> MMA : P written (and O rescaled)
-    static constexpr int kBarOFull = kBarPFull + 2;            // [2]  MMA -> softmax : P*V of this step retired
+    static constexpr int kBarPFull = kBarSFull + 2;            // [2][2] softmax -> MMA : first / second 64 keys of P written (O rescaled)
+    static constexpr int kBarOFull = kBarPFull + 4;            // [2]  MMA -> softmax : P*V of this step retired
     static constexpr int kNumBars = kBarOFull + 2;
     static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
     static constexpr int kBytes = kTmemPtrOff + 16;

@@ -296,6 +296,34 @@ __device__ __forceinline__ uint32_t mask_gt(uint32_t v, int idx, int lim) {
         : "=r"(d) : "r"(v), "r"(idx), "r"(lim));
     return d;
 }
+// exp2 on the FMA/ALU pipes for a pair of values (Cody-Waite split + degree-3 polynomial), used for a fraction of the
+// softmax exponentials so that MUFU.EX2 (16/clk/SM) is not the only pipe doing them:
+//   x = n + f, n = floor(x) via the 1.5*2^23 magic add in round-down mode, f in [0,1)
+//   2^f ~= 1 + f*(c1 + f*(c2 + f*c3))   (max relative error 8.6e-5, far below the 2^-9 rounding of a bf16 P)
+//   2^x = 2^f with n added to the exponent field (integer add of the magic sum's low bits shifted by 23)
+// Inputs are clamped at -127 (=> 2^-127, flushed to 0), which also makes -inf (masked scores) safe.
+__device__ __forceinline__ float2 ex2_emu2(float2 x) {
+    x.x = fmaxf(x.x, -127.f);
+    x.y = fmaxf(x.y, -127.f);
+    uint64_t ux, ut, un, uf, up;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ux) : "f"(x.x), "f"(x.y));
+    asm("{\n\t.reg .b64 m;\n\tmov.b64 m, {%2, %2};\n\tadd.rm.ftz.f32x2 %0, %1, m;\n\t}" : "=l"(ut) : "l"(ux), "f"(12582912.f));
+    asm("{\n\t.reg .b64 m;\n\tmov.b64 m, {%2, %2};\n\tadd.rn.ftz.f32x2 %0, %1, m;\n\t}" : "=l"(un) : "l"(ut), "f"(-12582912.f));
+    asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(uf) : "l"(ux), "l"(un));
+    asm("{\n\t.reg .b64 c1, c2, c3, one, t;\n\t"
+        "mov.b64 c3, {%2, %2};\n\tmov.b64 c2, {%3, %3};\n\tmov.b64 c1, {%4, %4};\n\tmov.b64 one, {%5, %5};\n\t"
+        "fma.rn.ftz.f32x2 t, %1, c3, c2;\n\t"
+        "fma.rn.ftz.f32x2 t, t, %1, c1;\n\t"
+        "fma.rn.ftz.f32x2 %0, t, %1, one;\n\t}"
+        : "=l"(up) : "l"(uf), "f"(0.07706617563962936f), "f"(0.22764593362808228f), "f"(0.6951165795326233f), "f"(1.0f));
+    uint32_t p0, p1, t0, t1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(up));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(ut));
+    float2 r;
+    r.x = __uint_as_float(p0 + (t0 << 23));
+    r.y = __uint_as_float(p1 + (t1 << 23));
+    return r;
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

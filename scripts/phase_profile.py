@@ -4,7 +4,7 @@ import ctypes, os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "flash-attention-cuda-c_b200")]
 import torch, fa_b200
-fa_b200.LIB_PATH = os.path.join(ROOT, "flash-attention-cuda-c_b200", "libfa_b200_prof.so")
+fa_b200.LIB_PATH = os.path.abspath(os.environ.get("FA_LIB", os.path.join(ROOT, "flash-attention-cuda-c_b200", "libfa_b200_prof.so")))
 L = fa_b200.lib()
 L.fa_debug_set_profile_buffer.argtypes = [ctypes.c_void_p]
 B, H, N, d, causal = [int(x) for x in (sys.argv[1:6] if len(sys.argv) > 5 else (8, 32, 8192, 128, 1))]
@@ -19,5 +19,5 @@ tiles = sum(min((N + 127) // 128, ((qb * 256 + 255) // 128 + 1)) if causal else 
 names = ["wait_S", "ld_S", "mask_max_rescale", "exp_pack_st", "st_drain_arrive", "loop_misc"]
 sm = {n: p[i] / (8 * tiles) for i, n in enumerate(names)}      # 8 softmax warps per CTA report, per kv iteration
 mma = {n: p[8 + i] / tiles for i, n in enumerate(["prologue(per CTA, amortised)", "wait_KV", "wait_P(both tiles)", "issue"])}
-print(json.dumps({"shape": [B, H, N, d, causal], "kv_iterations": tiles, "softmax_warp_cycles_per_kv_iteration": sm,
-                  "softmax_total": sum(sm.values()), "mma_thread_cycles_per_kv_iteration": mma, "mma_total": sum(mma.values())}, indent=1))
+print(json.dumps({"lib": os.path.basename(fa_b200.LIB_PATH), "shape": [B, H, N, d, causal], "kv_iterations": tiles, "softmax_warp_cycles_per_kv_iteration": sm,
+                  "softmax_total": sum(sm.values()), "mma_thread_cycles_per_kv_iteration": mma, "mma_total": sum(mma.values())}))
