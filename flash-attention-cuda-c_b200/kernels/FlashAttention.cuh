@@ -82,7 +82,7 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     } else {
         reg_dec<kOtherRegs>();
         if (warp == kMmaWarp) {
-            if (lane == 0) mmaIssuerThread<D, STAGES, DT>(smem_base, tmem_base, w, p.prof);
+            mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, w, p.prof);
         } else if (warp == kLoadWarp) {
             if (lane == 0) tmaLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, w);
         }

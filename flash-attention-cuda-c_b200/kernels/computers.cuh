@@ -29,12 +29,14 @@ constexpr uint32_t kTmemO0 = 256;    // O tile t at columns 256 + 128*t
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
 
 // ------------------------------------------------------------------------------------------------
-// MMA issuer: one thread.
+// MMA issuer: the whole warp walks the schedule (so that addresses and descriptors stay warp-uniform and live in
+// uniform registers); one elected lane issues each tcgen05.mma / tcgen05.commit.
 // Issue order per key tile j (t = query tile):  P_0V_j, Q_0K_{j+1}, P_1V_j, Q_1K_{j+1}
 // ------------------------------------------------------------------------------------------------
 template <int D, int STAGES, int DT>
-__device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tmem_base, const WorkItem& w,
-                                                unsigned long long* prof = nullptr) {
+__device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const WorkItem& w,
+                                              unsigned long long* prof = nullptr) {
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);   // tell the compiler it is warp-uniform
     using L = SmemLayout<D, STAGES>;
     constexpr uint32_t kFmt = (DT == kBF16) ? 1u : 0u;
     constexpr uint32_t idesc_qk = umma_idesc(kBlockM, kBlockN, kFmt, 0, 0);
@@ -55,7 +57,7 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
         for (int ks = 0; ks < D / 16; ++ks) {
             // 16 halfs = 32 B inside the 128-B swizzle row; the second 64 columns live one half (16 KiB) further
             const uint32_t off = ((ks / 4) * kHalfBytes + (ks % 4) * 32) >> 4;
-            umma_ss(d_tmem, a0 + off, b0 + off, idesc_qk, ks > 0);
+            if (elect_one_sync()) umma_ss(d_tmem, a0 + off, b0 + off, idesc_qk, ks > 0);
         }
     };
     // P_t V_j in two halves of 4 k-steps (64 keys each): the first half can start while the softmax warpgroup is still
@@ -68,12 +70,13 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
         for (int kk = 0; kk < kBlockN / 32; ++kk) {
             const int ks = half * (kBlockN / 32) + kk;
             // 16 key rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B
-            umma_ts(d_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (accumulate || ks > 0) ? 1u : 0u);
+            if (elect_one_sync()) umma_ts(d_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (accumulate || ks > 0) ? 1u : 0u);
         }
     };
     auto slot_addr = [&](int it) { return smem_base + L::kKVOff + (it % STAGES) * L::kKVTileBytes; };
     auto wait_full = [&](int it) { mbar_wait(bar(L::kBarKVFull + it % STAGES), (it / STAGES) & 1); };
-    auto release = [&](int it) { tc_commit(bar(L::kBarKVEmpty + it % STAGES)); };
+    auto commit = [&](uint32_t b) { if (elect_one_sync()) tc_commit(b); };
+    auto release = [&](int it) { commit(bar(L::kBarKVEmpty + it % STAGES)); };
 
     FA_PROF_DECL(4);
     mbar_wait(bar(L::kBarQFull), 0);
@@ -81,9 +84,9 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
     tc_fence_after();
     FA_PROF_MARK(0);                 // prologue: Q + K0 arrival
     issue_qk(0, slot_addr(0));
-    tc_commit(bar(L::kBarSFull + 0));
+    commit(bar(L::kBarSFull + 0));
     issue_qk(1, slot_addr(0));
-    tc_commit(bar(L::kBarSFull + 1));
+    commit(bar(L::kBarSFull + 1));
     release(0);
 
     for (int j = 0; j < w.n_kv; ++j) {
@@ -103,7 +106,7 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
             tc_fence_after();
             FA_PROF_MARK(2);
             issue_pv_half(t, slot_addr(it_v), j > 0, 1);
-            tc_commit(bar(L::kBarOFull + t));
+            commit(bar(L::kBarOFull + t));
             if (has_next) {
                 if (t == 0) {
                     FA_PROF_MARK(3);
@@ -112,14 +115,14 @@ __device__ __forceinline__ void mmaIssuerThread(uint32_t smem_base, uint32_t tme
                     FA_PROF_MARK(1);
                 }
                 issue_qk(t, slot_addr(it_k));
-                tc_commit(bar(L::kBarSFull + t));
+                commit(bar(L::kBarSFull + t));
             }
         }
         release(it_v);
         if (has_next) release(it_k);
     }
     FA_PROF_MARK(3);
-    FA_PROF_FLUSH(prof, 8, 4);
+    if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(prof, 8, 4);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -37,7 +37,7 @@ constexpr int kSoftmaxRegs = 208;
 constexpr int kOtherRegs = 88;
 // Of every 8 consecutive score pairs, this many take the FMA-pipe exp2 (ex2_emu2) instead of MUFU.EX2.
 #ifndef FA_EMU_PAIRS_PER_8
-#define FA_EMU_PAIRS_PER_8 3
+#define FA_EMU_PAIRS_PER_8 0
 #endif
 constexpr int kEmuPairsPer8 = FA_EMU_PAIRS_PER_8;
 

@@ -31,6 +31,10 @@ __global__ void k(float* out, long long* cyc, float seed) {
                                  asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[(i + 4) & 15]) : "f"(1.0001f), "f"(0.5f)); }
                 if (MODE == 7) { uint32_t u = __float_as_uint(a[i]); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u) : "r"(0x800000u), "r"(acc)); a[i] = __uint_as_float(u); }
                 if (MODE == 8) { asm volatile("add.rm.ftz.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(12582912.f)); }
+                if (MODE == 9) { uint32_t u = __float_as_uint(a[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u); }
+                if (MODE == 10) { uint32_t u = __float_as_uint(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u); }
+                if (MODE == 11) { uint32_t u = __float_as_uint(a[i]); uint32_t lo, hi; asm volatile("shl.b32 %0, %1, 16;" : "=r"(lo) : "r"(u)); asm volatile("and.b32 %0, %1, 0xffff0000;" : "=r"(hi) : "r"(u)); acc ^= lo + hi; }
+                if (MODE == 12) { uint32_t u = __float_as_uint(a[i]); asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i])); }
             }
         }
     }
@@ -45,12 +49,12 @@ __global__ void k(float* out, long long* cyc, float seed) {
 int main() {
     float* out; long long* cyc; cudaMalloc(&out, 148 * 256 * 4); cudaMallocManaged(&cyc, 16 * 8);
     const char* names[] = {"MUFU.EX2", "F2FP.BF16 pack", "FFMA", "FFMA2 (per packed instr)", "FMNMX3", "MUFU + F2FP interleaved (per pair)",
-                           "MUFU + 2 FFMA interleaved (per triple)", "IMAD", "FADD.RM"};
+                           "MUFU + 2 FFMA interleaved (per triple)", "IMAD", "FADD.RM", "ex2.bf16x2 (2 exps)", "ex2.f16x2 (2 exps)", "bf16x2 unpack (shl+and)", "tanh.f32"};
     for (int warps : {4, 8}) {
         printf("-- %d warps per CTA (%d per sub-partition), 148 CTAs\n", warps, warps / 4);
 #define RUN(M) k<M><<<148, warps * 32>>>(out, cyc, 0.5f); cudaDeviceSynchronize(); \
         printf("%-44s %.2f cycles per warp-instruction (group)\n", names[M], double(cyc[M]) / (256.0 * REP / (M == 3 ? 2 : 1)));
-        RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8)
+        RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) RUN(11) RUN(12)
     }
     return 0;
 }
