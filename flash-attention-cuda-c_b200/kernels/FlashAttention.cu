@@ -88,9 +88,31 @@ int make_tile_map(CUtensorMap* m, const void* base, int dtype, int B, int H, int
     return FA_OK;
 }
 
+// ---- work-item counters for the persistent kernel ------------------------------------------------------
+// One zeroed int per launch, taken round-robin from a per-device pool (so launches in flight on different streams do
+// not share a counter as long as fewer than kCounterSlots of them overlap).
+constexpr int kCounterSlots = 1024;
+int* next_counter(cudaStream_t st, int* sm_count_out) {
+    static std::mutex mu;
+    static int* pool[64] = {};
+    static int sms[64] = {};
+    static unsigned next[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pool[dev]) {
+        if (cudaMalloc(&pool[dev], kCounterSlots * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    }
+    int* c = pool[dev] + (next[dev]++ % kCounterSlots);
+    if (cudaMemsetAsync(c, 0, sizeof(int), st) != cudaSuccess) return nullptr;
+    *sm_count_out = sms[dev];
+    return c;
+}
+
 // ---- tcgen05 path ----------------------------------------------------------------------------------
 template <int D, int STAGES, int DT>
-int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p,
+int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, fa::FwdParams p,
                  cudaStream_t st) {
     using L = fa::SmemLayout<D, STAGES>;
     auto kern = fa::fwdSm100Kernel<D, STAGES, DT>;
@@ -109,8 +131,15 @@ int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
     }
     if (attr_err != cudaSuccess) return fail(FA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) -> %s", L::kDynamicBytes,
                                              cudaGetErrorString(attr_err));
-    const int rows_per_cta = fa::kTilesPerCta * fa::kBlockM;
-    dim3 grid((p.Nq + rows_per_cta - 1) / rows_per_cta, p.Hq, p.B);
+    const int rows_per_item = fa::kTilesPerCta * fa::kBlockM;
+    p.num_q_blocks = (p.Nq + rows_per_item - 1) / rows_per_item;
+    const long long items = (long long)p.num_q_blocks * p.Hq * p.B;
+    if (items > 0x7fffffffLL - 4096) return fail(FA_ERR_INVALID_ARGUMENT, "too many work items (%lld)", items);
+    p.total_items = (int)items;
+    int sm_count = 0;
+    p.sched_counter = next_counter(st, &sm_count);
+    if (!p.sched_counter) return fail(FA_ERR_CUDA, "work-item counter allocation failed");
+    const int grid = p.total_items < sm_count ? p.total_items : sm_count;   // persistent: one CTA per SM
     kern<<<grid, fa::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
     g_launches.fetch_add(1);
     FA_CUDA(cudaGetLastError());

@@ -27,7 +27,8 @@
 namespace fa {
 
 // ------------------------------------------------------------------------------------------------
-// B200 kernel: grid = (query blocks of 256 rows, Hq, B), 384 threads, 1 CTA / SM.
+// B200 kernel: persistent, grid = min(#SMs, work items), 384 threads, 1 CTA / SM; a work item is a 256-row query block
+// of one (batch, head), claimed from a global atomic counter (LPT order inside a head, (batch, head)-major overall).
 //   warps 0-3  softmax + correction + epilogue for query tile 0
 //   warps 4-7  softmax + correction + epilogue for query tile 1
 //   warp  8    MMA issuer (one thread)
@@ -50,6 +51,7 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == kMmaWarp && lane == 0) {
         const uint32_t bar0 = smem_base + L::kBarOff;
         mbar_init(bar0 + 8 * L::kBarQFull, 1);
+        mbar_init(bar0 + 8 * L::kBarQEmpty, 1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar0 + 8 * (L::kBarKVFull + s), 1);
             mbar_init(bar0 + 8 * (L::kBarKVEmpty + s), 1);
@@ -59,6 +61,9 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t), 128);
             mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t + 1), 128);
             mbar_init(bar0 + 8 * (L::kBarOFull + t), 1);
+            mbar_init(bar0 + 8 * (L::kBarOFree + t), 128);
+            mbar_init(bar0 + 8 * (L::kBarSchedFull + t), 1);
+            mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 1 + kSoftmaxWarps);   // MMA warp + every softmax warp
         }
         fence_mbar_init();
     } else if (warp == kLoadWarp && lane == 0) {
@@ -74,17 +79,15 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const WorkItem w = decode_work(p);
-
     if (warp < kSoftmaxWarps) {
         reg_inc<kSoftmaxRegs>();
-        softmaxWarpgroup<D, STAGES, DT>(smem_base, tmem_base, w, p, warp / 4);
+        softmaxWarpgroup<D, STAGES, DT>(smem_base, tmem_base, p, warp / 4);
     } else {
         reg_dec<kOtherRegs>();
         if (warp == kMmaWarp) {
-            mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, w, p.prof);
+            mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p);
         } else if (warp == kLoadWarp) {
-            if (lane == 0) tmaLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, w);
+            if (lane == 0) tmaLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, p);
         }
     }
 

@@ -30,12 +30,11 @@ constexpr float kRescaleThreshold = 8.0f;   // log2 units
 
 // ------------------------------------------------------------------------------------------------
 // MMA issuer: the whole warp walks the schedule (so that addresses and descriptors stay warp-uniform and live in
-// uniform registers); one elected lane issues each tcgen05.mma / tcgen05.commit.
-// Issue order per key tile j (t = query tile):  P_0V_j, Q_0K_{j+1}, P_1V_j, Q_1K_{j+1}
+// uniform registers); one elected lane issues each tcgen05.mma / tcgen05.commit.  Persistent: loops over the work
+// items the producer publishes.  Issue order per key tile j (t = query tile):  P_0V_j, Q_0K_{j+1}, P_1V_j, Q_1K_{j+1}
 // ------------------------------------------------------------------------------------------------
 template <int D, int STAGES, int DT>
-__device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const WorkItem& w,
-                                              unsigned long long* prof = nullptr) {
+__device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);   // tell the compiler it is warp-uniform
     using L = SmemLayout<D, STAGES>;
     constexpr uint32_t kFmt = (DT == kBF16) ? 1u : 0u;
@@ -43,8 +42,6 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
     constexpr uint32_t idesc_pv = umma_idesc(kBlockM, D, kFmt, 0, 1);
     const uint32_t bar0 = smem_base + L::kBarOff;
     auto bar = [&](int i) { return bar0 + 8u * uint32_t(i); };
-
-    if (w.n_kv <= 0) return;
 
     // Descriptor templates with a zero start address; the 14-bit address field (bytes >> 4) is added per MMA.
     const uint64_t desc_k_major = umma_desc_sw128(0, 16, 1024);             // Q and K tiles (K-major)
@@ -79,217 +76,262 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
     auto release = [&](int it) { commit(bar(L::kBarKVEmpty + it % STAGES)); };
 
     FA_PROF_DECL(4);
-    mbar_wait(bar(L::kBarQFull), 0);
-    wait_full(0);
-    tc_fence_after();
-    FA_PROF_MARK(0);                 // prologue: Q + K0 arrival
-    issue_qk(0, slot_addr(0));
-    commit(bar(L::kBarSFull + 0));
-    issue_qk(1, slot_addr(0));
-    commit(bar(L::kBarSFull + 1));
-    release(0);
+    int it0 = 0;              // ring position of this item's K_0  (K_j = it0 + 2j, V_j = it0 + 2j + 1)
+    int kq = 0;               // items with work so far (Q loads consumed)
+    int st0 = 0, st1 = 0;     // key tiles processed so far, per query tile (barrier phase bookkeeping)
+    int ko0 = 0, ko1 = 0;     // items in which the query tile had work (O hand-back bookkeeping)
+    for (int k = 0;; ++k) {
+        const int item = fetch_item<D, STAGES>(smem_base, k);
+        if (item < 0) break;
+        const WorkItem w = decode_item(p, item);
+        const int n = w.n_kv;
+        if (n <= 0) continue;
 
-    for (int j = 0; j < w.n_kv; ++j) {
-        const int it_v = 2 * j + 1, it_k = 2 * j + 2;
-        const bool has_next = j + 1 < w.n_kv;
-        FA_PROF_MARK(3);             // issue + bookkeeping
-        wait_full(it_v);
-        FA_PROF_MARK(1);             // waiting for V/K tiles
+        mbar_wait(bar(L::kBarQFull), kq & 1);
+        ++kq;
+        wait_full(it0);
+        tc_fence_after();
+        FA_PROF_MARK(0);                 // Q + K0 arrival
 #pragma unroll
-        for (int t = 0; t < kTilesPerCta; ++t) {
-            mbar_wait(bar(L::kBarPFull + 2 * t), j & 1);
-            tc_fence_after();
-            FA_PROF_MARK(2);         // waiting for P
-            issue_pv_half(t, slot_addr(it_v), j > 0, 0);
-            FA_PROF_MARK(3);
-            mbar_wait(bar(L::kBarPFull + 2 * t + 1), j & 1);
-            tc_fence_after();
-            FA_PROF_MARK(2);
-            issue_pv_half(t, slot_addr(it_v), j > 0, 1);
-            commit(bar(L::kBarOFull + t));
-            if (has_next) {
-                if (t == 0) {
-                    FA_PROF_MARK(3);
-                    wait_full(it_k);
-                    tc_fence_after();
-                    FA_PROF_MARK(1);
-                }
-                issue_qk(t, slot_addr(it_k));
+        for (int t = 0; t < kTilesPerCta; ++t)
+            if (w.n_tile(t) > 0) {
+                issue_qk(t, slot_addr(it0));
                 commit(bar(L::kBarSFull + t));
             }
+        if (n == 1) commit(bar(L::kBarQEmpty));      // that was the item's last use of the Q tiles
+        release(it0);
+
+        for (int j = 0; j < n; ++j) {
+            const int it_v = it0 + 2 * j + 1, it_k = it0 + 2 * j + 2;
+            const bool has_next = j + 1 < n;
+            FA_PROF_MARK(3);             // issue + bookkeeping
+            wait_full(it_v);
+            FA_PROF_MARK(1);             // waiting for K/V tiles
+            bool k_ready = false;
+#pragma unroll
+            for (int t = 0; t < kTilesPerCta; ++t) {
+                if (j < w.n_tile(t)) {
+                    const uint32_t ph = ((t == 0 ? st0 : st1) + j) & 1;
+                    const int ko_t = t == 0 ? ko0 : ko1;
+                    // the previous item's epilogue must have read O out of TMEM before this item overwrites it
+                    if (j == 0 && ko_t > 0) mbar_wait(bar(L::kBarOFree + t), (ko_t - 1) & 1);
+                    mbar_wait(bar(L::kBarPFull + 2 * t), ph);
+                    tc_fence_after();
+                    FA_PROF_MARK(2);     // waiting for P
+                    issue_pv_half(t, slot_addr(it_v), j > 0, 0);
+                    FA_PROF_MARK(3);
+                    mbar_wait(bar(L::kBarPFull + 2 * t + 1), ph);
+                    tc_fence_after();
+                    FA_PROF_MARK(2);
+                    issue_pv_half(t, slot_addr(it_v), j > 0, 1);
+                    commit(bar(L::kBarOFull + t));
+                }
+                if (j + 1 < w.n_tile(t)) {
+                    if (!k_ready) {
+                        FA_PROF_MARK(3);
+                        wait_full(it_k);
+                        tc_fence_after();
+                        FA_PROF_MARK(1);
+                        k_ready = true;
+                    }
+                    issue_qk(t, slot_addr(it_k));
+                    commit(bar(L::kBarSFull + t));
+                }
+            }
+            if (j + 2 == n) commit(bar(L::kBarQEmpty));   // K_{n-1} was the last tile multiplied with Q
+            release(it_v);
+            if (has_next) {
+                if (!k_ready) wait_full(it_k);             // (cannot happen: the busiest tile always needs K_{j+1})
+                release(it_k);
+            }
         }
-        release(it_v);
-        if (has_next) release(it_k);
+        st0 += w.n_tile0;
+        st1 += w.n_tile1;
+        ko0 += w.n_tile0 > 0 ? 1 : 0;
+        ko1 += w.n_tile1 > 0 ? 1 : 0;
+        it0 += 2 * n;
     }
     FA_PROF_MARK(3);
-    if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(prof, 8, 4);
+    if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 8, 4);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Softmax warpgroup for query tile t (128 threads, one score row each), including the lazy O
-// rescale and the epilogue (O/l -> global, optional LSE).
+// Softmax warpgroup for query tile t (128 threads, one score row each), including the lazy O rescale and the
+// epilogue (O/l -> global, optional LSE).  Persistent: loops over the published work items; the epilogue of one item
+// overlaps the next item's first Q K^T.
 // ------------------------------------------------------------------------------------------------
 template <int D, int STAGES, int DT>
-__device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const WorkItem& w,
-                                                 const FwdParams& p, int t) {
+__device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, int t) {
     using L = SmemLayout<D, STAGES>;
     const uint32_t bar0 = smem_base + L::kBarOff;
     const uint32_t s_full = bar0 + 8u * (L::kBarSFull + t);
     const uint32_t p_full0 = bar0 + 8u * (L::kBarPFull + 2 * t);
     const uint32_t p_full1 = p_full0 + 8u;
     const uint32_t o_full = bar0 + 8u * (L::kBarOFull + t);
+    const uint32_t o_free = bar0 + 8u * (L::kBarOFree + t);
 
     const int warp_in_wg = (threadIdx.x / 32) & 3;
     const int lane = threadIdx.x & 31;
     const uint32_t lane_base = uint32_t(warp_in_wg * 32) << 16;
     const uint32_t tS = tmem_base + lane_base + kTmemS0 + 128u * t;
     const uint32_t tO = tmem_base + lane_base + kTmemO0 + 128u * t;
-
-    const int tile_row0 = w.q0 + t * kBlockM;
-    const int row = tile_row0 + warp_in_wg * 32 + lane;
-
     const float c = p.scale_log2;
-    float m_run = -INFINITY;   // max in use, in raw (unscaled) score units
-    float l_run = 0.f;
 
     FA_PROF_DECL(6);
-    for (int j = 0; j < w.n_kv; ++j) {
-        FA_PROF_MARK(5);             // loop overhead / l update
-        mbar_wait(s_full, j & 1);
-        tc_fence_after();
-        FA_PROF_MARK(0);             // waiting for S
+    int st = 0;      // key tiles this warpgroup has processed so far (barrier phase bookkeeping)
+    for (int k = 0;; ++k) {
+        const int item = fetch_item<D, STAGES>(smem_base, k);
+        if (item < 0) break;
+        const WorkItem w = decode_item(p, item);
+        const int n = w.n_tile(t);
+        const int tile_row0 = w.q0 + t * kBlockM;
+        const int row = tile_row0 + warp_in_wg * 32 + lane;
 
-        uint32_t r[kBlockN];
-#pragma unroll
-        for (int q = 0; q < kBlockN / 32; ++q) tmem_ld32(tS + 32u * q, r + 32 * q);
-        tc_wait_ld();
-        FA_PROF_MARK(1);             // tcgen05.ld of the score row
+        float m_run = -INFINITY;   // max in use, in raw (unscaled) score units
+        float l_run = 0.f;
 
-        const int kv0 = j * kBlockN;
-        const bool need_mask = (kv0 + kBlockN > p.Nk) || (p.causal && (kv0 + kBlockN - 1 > tile_row0 + p.causal_off));
-        if (need_mask) {
-            const int lim_c = p.causal ? (row + p.causal_off) : 0x7fffffff;
-            const int lim = min(lim_c, p.Nk - 1) - kv0;   // columns c > lim are masked
-#pragma unroll
-            for (int cc = 0; cc < kBlockN; ++cc) r[cc] = mask_gt(r[cc], cc, lim);   // -inf where cc > lim
-        }
+        for (int j = 0; j < n; ++j) {
+            const uint32_t ph = (st + j) & 1;
+            FA_PROF_MARK(5);             // loop overhead / l update / epilogue
+            mbar_wait(s_full, ph);
+            tc_fence_after();
+            FA_PROF_MARK(0);             // waiting for S
 
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            uint32_t r[kBlockN];
 #pragma unroll
-        for (int cc = 0; cc < kBlockN; cc += 8) {
-            mx0 = max3(mx0, __uint_as_float(r[cc + 0]), __uint_as_float(r[cc + 1]));
-            mx1 = max3(mx1, __uint_as_float(r[cc + 2]), __uint_as_float(r[cc + 3]));
-            mx2 = max3(mx2, __uint_as_float(r[cc + 4]), __uint_as_float(r[cc + 5]));
-            mx3 = max3(mx3, __uint_as_float(r[cc + 6]), __uint_as_float(r[cc + 7]));
-        }
-        const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(fmaxf(mx2, mx3), m_run));
+            for (int q = 0; q < kBlockN / 32; ++q) tmem_ld32(tS + 32u * q, r + 32 * q);
+            tc_wait_ld();
+            FA_PROF_MARK(1);             // tcgen05.ld of the score row
 
-        if (j == 0) {
-            m_run = m_new;
-        } else {
-            // lazy rescale: (m_new - m_run) is NaN when both are -inf -> compares false
-            const bool grow = (m_new - m_run) * c > kRescaleThreshold;
-            if (__any_sync(0xffffffffu, grow)) {
-                const float f = grow ? ex2_approx((m_run - m_new) * c) : 1.0f;
-                mbar_wait(o_full, (j - 1) & 1);
-                tc_fence_after();
+            const int kv0 = j * kBlockN;
+            const bool need_mask = (kv0 + kBlockN > p.Nk) || (p.causal && (kv0 + kBlockN - 1 > tile_row0 + p.causal_off));
+            if (need_mask) {
+                const int lim_c = p.causal ? (row + p.causal_off) : 0x7fffffff;
+                const int lim = min(lim_c, p.Nk - 1) - kv0;   // columns c > lim are masked
 #pragma unroll
-                for (int q = 0; q < D / 32; ++q) {
-                    uint32_t o[32];
-                    tmem_ld32(tO + 32u * q, o);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                    tmem_st32(tO + 32u * q, o);
-                }
-                l_run *= f;
-                if (grow) m_run = m_new;
+                for (int cc = 0; cc < kBlockN; ++cc) r[cc] = mask_gt(r[cc], cc, lim);   // -inf where cc > lim
             }
-        }
-        FA_PROF_MARK(2);             // mask + row max + (rare) O rescale
-        const float m_safe = (m_run == -INFINITY) ? 0.f : m_run;
-        const float2 c2 = make_float2(c, c);
-        const float2 nm2 = make_float2(-m_safe * c, -m_safe * c);
 
-        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-        // exp2 of one score pair: MUFU.EX2 for most pairs, FMA-pipe emulation for kEmuPairsPer8 of every 8
-        auto exp_pair = [&](int col) -> float2 {
-            float2 x = fma2(make_float2(__uint_as_float(r[col]), __uint_as_float(r[col + 1])), c2, nm2);
-            if (((col / 2) % 8) * 3 % 8 < kEmuPairsPer8) {     // spread the emulated pairs evenly over the group of 8
-                x = ex2_emu2(x);
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int cc = 0; cc < kBlockN; cc += 8) {
+                mx0 = max3(mx0, __uint_as_float(r[cc + 0]), __uint_as_float(r[cc + 1]));
+                mx1 = max3(mx1, __uint_as_float(r[cc + 2]), __uint_as_float(r[cc + 3]));
+                mx2 = max3(mx2, __uint_as_float(r[cc + 4]), __uint_as_float(r[cc + 5]));
+                mx3 = max3(mx3, __uint_as_float(r[cc + 6]), __uint_as_float(r[cc + 7]));
+            }
+            const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(fmaxf(mx2, mx3), m_run));
+
+            if (j == 0) {
+                m_run = m_new;
             } else {
-                x.x = ex2_approx(x.x);
-                x.y = ex2_approx(x.y);
-            }
-            return x;
-        };
-        // 32 scores -> 16 packed columns
-        auto exp_quarter = [&](int qt, uint32_t* pk) {
+                // lazy rescale: (m_new - m_run) is NaN when both are -inf -> compares false
+                const bool grow = (m_new - m_run) * c > kRescaleThreshold;
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float f = grow ? ex2_approx((m_run - m_new) * c) : 1.0f;
+                    mbar_wait(o_full, ph ^ 1);      // P V of the previous key tile has retired
+                    tc_fence_after();
 #pragma unroll
-            for (int cc = 0; cc < 32; cc += 4) {
-                const float2 x0 = exp_pair(32 * qt + cc), x1 = exp_pair(32 * qt + cc + 2);
-                s0 = add2(s0, x0);
-                s1 = add2(s1, x1);
-                pk[cc / 2 + 0] = pack16<DT>(x0.x, x0.y);
-                pk[cc / 2 + 1] = pack16<DT>(x1.x, x1.y);
+                    for (int q = 0; q < D / 32; ++q) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + 32u * q, o);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                        tmem_st32(tO + 32u * q, o);
+                    }
+                    l_run *= f;
+                    if (grow) m_run = m_new;
+                }
             }
-        };
-        {
-            uint32_t pk[32];
-            exp_quarter(0, pk);
-            exp_quarter(1, pk + 16);
-            tmem_st32(tS, pk);                 // keys 0..63 of P
-        }
-        {
-            uint32_t pk[32];
-            exp_quarter(2, pk);
-            tc_wait_st();                      // first half landed while quarter 2 was computed
-            tc_fence_before();
-            mbar_arrive(p_full0);              // MMA may start P V on keys 0..63
-            exp_quarter(3, pk + 16);
-            tmem_st32(tS + 32u, pk);           // keys 64..127 of P
-        }
-        FA_PROF_MARK(3);             // exp2 / pack / tcgen05.st issue
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(p_full1);
-        FA_PROF_MARK(4);             // store drain + arrive
+            FA_PROF_MARK(2);             // mask + row max + (rare) O rescale
+            const float m_safe = (m_run == -INFINITY) ? 0.f : m_run;
+            const float2 c2 = make_float2(c, c);
+            const float2 nm2 = make_float2(-m_safe * c, -m_safe * c);
 
-        l_run += (s0.x + s0.y) + (s1.x + s1.y);
+            float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+            // exp2 of one score pair: MUFU.EX2 for most pairs, FMA-pipe emulation for kEmuPairsPer8 of every 8
+            auto exp_pair = [&](int col) -> float2 {
+                float2 x = fma2(make_float2(__uint_as_float(r[col]), __uint_as_float(r[col + 1])), c2, nm2);
+                if (((col / 2) % 8) * 3 % 8 < kEmuPairsPer8) {     // spread the emulated pairs evenly over the group of 8
+                    x = ex2_emu2(x);
+                } else {
+                    x.x = ex2_approx(x.x);
+                    x.y = ex2_approx(x.y);
+                }
+                return x;
+            };
+            // 32 scores -> 16 packed columns
+            auto exp_quarter = [&](int qt, uint32_t* pk) {
+#pragma unroll
+                for (int cc = 0; cc < 32; cc += 4) {
+                    const float2 x0 = exp_pair(32 * qt + cc), x1 = exp_pair(32 * qt + cc + 2);
+                    s0 = add2(s0, x0);
+                    s1 = add2(s1, x1);
+                    pk[cc / 2 + 0] = pack16<DT>(x0.x, x0.y);
+                    pk[cc / 2 + 1] = pack16<DT>(x1.x, x1.y);
+                }
+            };
+            {
+                uint32_t pk[32];
+                exp_quarter(0, pk);
+                exp_quarter(1, pk + 16);
+                tmem_st32(tS, pk);                 // keys 0..63 of P
+            }
+            {
+                uint32_t pk[32];
+                exp_quarter(2, pk);
+                tc_wait_st();                      // first half landed while quarter 2 was computed
+                tc_fence_before();
+                mbar_arrive(p_full0);              // MMA may start P V on keys 0..63
+                exp_quarter(3, pk + 16);
+                tmem_st32(tS + 32u, pk);           // keys 64..127 of P
+            }
+            FA_PROF_MARK(3);             // exp2 / pack / tcgen05.st issue
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(p_full1);
+            FA_PROF_MARK(4);             // store drain + arrive
+
+            l_run += (s0.x + s0.y) + (s1.x + s1.y);
+        }
+
+        // ---- epilogue: O / l -> global ----
+        const bool row_ok = row < p.Nq;
+        const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+        uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)w.b * p.o_stride_b + (long long)w.h * p.o_stride_h +
+                         (long long)row * p.o_stride_n;
+        if (n > 0) {
+            mbar_wait(o_full, (st + n - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < D / 32; ++q) {
+                uint32_t o[32];
+                tmem_ld32(tO + 32u * q, o);
+                tc_wait_ld();
+                uint32_t h[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    h[i] = pack16<DT>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        st_global_v4(orow + 32 * q + 8 * i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(o_free);         // O columns may be overwritten by the next item's first P V
+        } else if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) st_global_v4(orow + 8 * i, 0u, 0u, 0u, 0u);
+        }
+        if (p.lse != nullptr && row_ok) {
+            const float m_safe = (m_run == -INFINITY) ? 0.f : m_run;
+            p.lse[((long long)w.b * p.Hq + w.h) * p.Nq + row] = (l_run > 0.f) ? (m_safe * p.scale + logf(l_run)) : -INFINITY;
+        }
+        st += n;
     }
     if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 0, 6);
-
-    // ---- epilogue: O / l -> global ----
-    const bool row_ok = row < p.Nq;
-    const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-    uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)w.b * p.o_stride_b + (long long)w.h * p.o_stride_h +
-                     (long long)row * p.o_stride_n;
-    if (w.n_kv > 0) {
-        mbar_wait(o_full, (w.n_kv - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < D / 32; ++q) {
-            uint32_t o[32];
-            tmem_ld32(tO + 32u * q, o);
-            tc_wait_ld();
-            uint32_t h[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                h[i] = pack16<DT>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
-            if (row_ok) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    st_global_v4(orow + 32 * q + 8 * i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-            }
-        }
-    } else if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < D / 8; ++i) st_global_v4(orow + 8 * i, 0u, 0u, 0u, 0u);
-    }
-    if (p.lse != nullptr && row_ok) {
-        const float m_safe = (m_run == -INFINITY) ? 0.f : m_run;
-        p.lse[((long long)w.b * p.Hq + w.h) * p.Nq + row] = (l_run > 0.f) ? (m_safe * p.scale + logf(l_run)) : -INFINITY;
-    }
     tc_fence_before();
 }
 

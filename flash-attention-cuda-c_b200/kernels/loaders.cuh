@@ -8,8 +8,9 @@
 // 128-row tiles into 128B-swizzled shared memory; completion is signalled on mbarriers
 // (expect_tx / complete_tx), and slots are handed back by tcgen05.commit from the MMA issuer.
 //
+// The kernel is persistent: one CTA per SM walks a queue of work items (256-row query blocks).
 // Shared memory map (all tile buffers 1024-B aligned, required by SWIZZLE_128B):
-//   [ Q tile 0 | Q tile 1 | KV ring slot 0 .. slot S-1 | mbarriers | tmem base ]
+//   [ Q tile 0 | Q tile 1 | KV ring slot 0 .. slot S-1 | mbarriers | work-item slots | tmem base ]
 // A 128 x D tile of 16-bit elements is stored as D/64 "halves"; half h holds columns [64h, 64h+64)
 // as 128 rows of 128 bytes (row r at byte r*128, 16-byte chunks XOR-swizzled by r%8) — exactly
 // what a TMA box of {64, 128} with CU_TENSOR_MAP_SWIZZLE_128B writes and what the UMMA
@@ -51,6 +52,9 @@ struct FwdParams {
     int causal;              // 0/1
     int causal_off;          // Nk - Nq: key j visible to query i iff j <= i + causal_off
     int q_heads_per_kv;      // Hq / Hkv
+    int num_q_blocks;        // 256-row query blocks per (batch, head)
+    int total_items;         // B * Hq * num_q_blocks work items
+    int* sched_counter;      // device int, zero at launch: next work item = gridDim.x + atomicAdd(counter, 1)
     unsigned long long* prof; // FA_PHASE_PROFILE builds only: per-phase cycle counters (see scripts/phase_profile.py)
 };
 
@@ -62,84 +66,131 @@ struct SmemLayout {
     static constexpr int kKVOff = kTilesPerCta * kQTileBytes;
     static constexpr int kBarOff = kKVOff + STAGES * kKVTileBytes;
     // barrier indices
-    static constexpr int kBarQFull = 0;
-    static constexpr int kBarKVFull = 1;
+    static constexpr int kBarQFull = 0;                        //        TMA -> MMA     : both query tiles landed
+    static constexpr int kBarQEmpty = 1;                       //        MMA -> TMA     : last Q K^T of the item retired
+    static constexpr int kBarKVFull = 2;
     static constexpr int kBarKVEmpty = kBarKVFull + STAGES;
-    static constexpr int kBarSFull = kBarKVEmpty + STAGES;     // [2]  MMA -> softmax : S tile ready in TMEM
+    static constexpr int kBarSFull = kBarKVEmpty + STAGES;     // [2]    MMA -> softmax : S tile ready in TMEM
     static constexpr int kBarPFull = kBarSFull + 2;            // [2][2] softmax -> MMA : first / second 64 keys of P written (O rescaled)
-    static constexpr int kBarOFull = kBarPFull + 4;            // [2]  MMA -> softmax : P*V of this step retired
-    static constexpr int kNumBars = kBarOFull + 2;
-    static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+    static constexpr int kBarOFull = kBarPFull + 4;            // [2]    MMA -> softmax : P*V of this step retired
+    static constexpr int kBarOFree = kBarOFull + 2;            // [2]    softmax -> MMA : epilogue has read O out of TMEM
+    static constexpr int kBarSchedFull = kBarOFree + 2;        // [2]    TMA -> all     : next work item published
+    static constexpr int kBarSchedEmpty = kBarSchedFull + 2;   // [2]    all -> TMA     : work item slot consumed
+    static constexpr int kNumBars = kBarSchedEmpty + 2;
+    static constexpr int kSchedItemOff = kBarOff + kNumBars * 8;   // int[2]
+    static constexpr int kTmemPtrOff = kSchedItemOff + 8;
     static constexpr int kBytes = kTmemPtrOff + 16;
     static constexpr int kDynamicBytes = kBytes + 1024;        // slack for manual 1024-B alignment
 };
 
-// Work item of one CTA.
+// One work item: a 256-row query block of one (batch, head).
 struct WorkItem {
     int b, h, h_kv;
-    int q0;        // first query row of the CTA's 256-row block
-    int n_kv;      // number of 128-row key/value tiles to visit
+    int q0;        // first query row of the block
+    int n_kv;      // number of 128-row key/value tiles the block visits (that of its busiest query tile)
+    int n_tile0, n_tile1;   // tiles each query tile takes part in (causal: the early tile stops one sooner)
+    __device__ __forceinline__ int n_tile(int t) const { return t == 0 ? n_tile0 : n_tile1; }
 };
 
-__device__ __forceinline__ WorkItem decode_work(const FwdParams& p) {
+// Items are numbered (batch, head)-major so that CTAs running at the same time share K/V through L2; inside a head
+// the heavy (late) causal query blocks come first, which makes the dynamic scheduler an LPT queue.
+__device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
     WorkItem w;
-    // Heavy (late) causal query blocks first: the hardware block scheduler then acts as an LPT queue.
-    const int qb = p.causal ? (int(gridDim.x) - 1 - int(blockIdx.x)) : int(blockIdx.x);
-    w.h = blockIdx.y;
-    w.b = blockIdx.z;
+    const int bh = item / p.num_q_blocks;
+    const int r = item - bh * p.num_q_blocks;
+    const int qb = p.causal ? (p.num_q_blocks - 1 - r) : r;
+    w.b = bh / p.Hq;
+    w.h = bh - w.b * p.Hq;
     w.h_kv = w.h / p.q_heads_per_kv;
     w.q0 = qb * (kTilesPerCta * kBlockM);
-    int n = (p.Nk + kBlockN - 1) / kBlockN;
-    if (p.causal) {
-        const int last_col = w.q0 + kTilesPerCta * kBlockM - 1 + p.causal_off;   // last key any row of the block may see
-        const int n_c = last_col < 0 ? 0 : last_col / kBlockN + 1;
-        n = n_c < n ? n_c : n;
+    const int n_all = (p.Nk + kBlockN - 1) / kBlockN;
+    w.n_kv = 0;
+#pragma unroll
+    for (int t = 0; t < kTilesPerCta; ++t) {
+        int n = n_all;
+        if (p.causal) {
+            const int last_col = w.q0 + (t + 1) * kBlockM - 1 + p.causal_off;   // last key any row of the tile may see
+            const int n_c = last_col < 0 ? 0 : last_col / kBlockN + 1;
+            n = n_c < n ? n_c : n;
+        }
+        if (w.q0 + t * kBlockM >= p.Nq) n = 0;    // tile entirely past the end of the sequence
+        if (t == 0) w.n_tile0 = n; else w.n_tile1 = n;
+        w.n_kv = n > w.n_kv ? n : w.n_kv;
     }
-    w.n_kv = n;
     return w;
 }
 
-// Producer: a single thread.  Q tiles once, then K_j, V_j for j = 0..n_kv-1 through the ring.
+// Consumer side of the work-item hand-off (whole warp): returns the item index, or -1 when the queue is drained.
+template <int D, int STAGES>
+__device__ __forceinline__ int fetch_item(uint32_t smem_base, int k) {
+    using L = SmemLayout<D, STAGES>;
+    const uint32_t bar0 = smem_base + L::kBarOff;
+    const int slot = k & 1;
+    mbar_wait(bar0 + 8 * (L::kBarSchedFull + slot), (k >> 1) & 1);
+    int item;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(item) : "r"(smem_base + L::kSchedItemOff + 4 * slot) : "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar0 + 8 * (L::kBarSchedEmpty + slot));
+    return __shfl_sync(0xffffffffu, item, 0);
+}
+
+// Producer: a single thread.  It is also the scheduler: it claims the CTA's next work item (the first one is
+// blockIdx.x, later ones come from a global atomic counter), publishes it to the other roles one item ahead, then
+// streams that item's tiles: Q tiles once, then K_j, V_j for j = 0..n_kv-1 through the ring.
 template <int D, int STAGES>
 __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CUtensorMap* tmK,
-                                                const CUtensorMap* tmV, uint32_t smem_base,
-                                                const WorkItem& w) {
+                                                const CUtensorMap* tmV, uint32_t smem_base, const FwdParams& p) {
     using L = SmemLayout<D, STAGES>;
     constexpr int kHalves = D / kHalfCols;
     const uint32_t bar0 = smem_base + L::kBarOff;
-
-    // Q: both tiles on one barrier.
     const uint32_t q_full = bar0 + 8 * L::kBarQFull;
-    mbar_expect_tx(q_full, kTilesPerCta * L::kQTileBytes);
-#pragma unroll
-    for (int t = 0; t < kTilesPerCta; ++t)
-#pragma unroll
-        for (int hf = 0; hf < kHalves; ++hf)
-            tma_load_4d_hint(tmQ, smem_base + L::kQOff + t * L::kQTileBytes + hf * kHalfBytes, q_full,
-                             hf * kHalfCols, w.q0 + t * kBlockM, w.h, w.b, kEvictFirst);
+    const uint32_t q_empty = bar0 + 8 * L::kBarQEmpty;
 
-    int it = 0;
-    for (int j = 0; j < w.n_kv; ++j) {
+    int it = 0;      // K/V ring fills so far
+    int kq = 0;      // Q loads so far
+    int item = blockIdx.x;
+    for (int k = 0;; ++k) {
+        const int slot = k & 1;
+        mbar_wait(bar0 + 8 * (L::kBarSchedEmpty + slot), ((k >> 1) & 1) ^ 1);
+        const int pub = item < p.total_items ? item : -1;
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(smem_base + L::kSchedItemOff + 4 * slot), "r"(pub) : "memory");
+        mbar_arrive(bar0 + 8 * (L::kBarSchedFull + slot));
+        if (pub < 0) break;
+        const WorkItem w = decode_item(p, item);
+        if (w.n_kv > 0) {
+            mbar_wait(q_empty, (kq & 1) ^ 1);      // the previous item's last Q K^T has retired
+            ++kq;
+            mbar_expect_tx(q_full, kTilesPerCta * L::kQTileBytes);
 #pragma unroll
-        for (int kv = 0; kv < 2; ++kv, ++it) {
-            const int slot = it % STAGES;
-            const uint32_t parity = (it / STAGES) & 1;
-            const uint32_t full = bar0 + 8 * (L::kBarKVFull + slot);
-            const uint32_t empty = bar0 + 8 * (L::kBarKVEmpty + slot);
-            mbar_wait(empty, parity ^ 1);
-            mbar_expect_tx(full, L::kKVTileBytes);
-            const CUtensorMap* tm = kv == 0 ? tmK : tmV;
+            for (int t = 0; t < kTilesPerCta; ++t)
 #pragma unroll
-            for (int hf = 0; hf < kHalves; ++hf)
-                tma_load_4d_hint(tm, smem_base + L::kKVOff + slot * L::kKVTileBytes + hf * kHalfBytes, full,
-                                 hf * kHalfCols, j * kBlockN, w.h_kv, w.b, kEvictLast);
+                for (int hf = 0; hf < kHalves; ++hf)
+                    tma_load_4d_hint(tmQ, smem_base + L::kQOff + t * L::kQTileBytes + hf * kHalfBytes, q_full,
+                                     hf * kHalfCols, w.q0 + t * kBlockM, w.h, w.b, kEvictFirst);
+            for (int j = 0; j < w.n_kv; ++j) {
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t parity = (it / STAGES) & 1;
+                    const uint32_t full = bar0 + 8 * (L::kBarKVFull + s);
+                    mbar_wait(bar0 + 8 * (L::kBarKVEmpty + s), parity ^ 1);
+                    mbar_expect_tx(full, L::kKVTileBytes);
+                    const CUtensorMap* tm = kv == 0 ? tmK : tmV;
+#pragma unroll
+                    for (int hf = 0; hf < kHalves; ++hf)
+                        tma_load_4d_hint(tm, smem_base + L::kKVOff + s * L::kKVTileBytes + hf * kHalfBytes, full,
+                                         hf * kHalfCols, j * kBlockN, w.h_kv, w.b, kEvictLast);
+                }
+            }
         }
+        item = int(gridDim.x) + atomicAdd(p.sched_counter, 1);
     }
     // Tail: wait until the consumer has handed back the last fills, so that no tcgen05.commit arrive is still in
     // flight towards this CTA's shared memory when the CTA exits.
     const int total = it;
     for (int i = (total > STAGES ? total - STAGES : 0); i < total; ++i)
         mbar_wait(bar0 + 8 * (L::kBarKVEmpty + i % STAGES), (i / STAGES) & 1);
+    if (kq > 0) mbar_wait(q_empty, (kq - 1) & 1);
 }
 
 }  // namespace fa
