@@ -57,7 +57,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms from the last warm-up steps through the timed region
+    (the timed region of the default run is < 0.1 s, so the sampler is started during warm-up to be sure it is
+    already delivering samples under load when timing starts)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -66,7 +68,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -79,7 +81,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons, power = [], [], set(), []
         for r in self.rows:
@@ -90,8 +92,11 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 continue
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        load = [c for c, w in zip(sm, power) if w >= 0.5 * max(power)] if power else []
+        return {"sm_mhz": statistics.median(load) if load else (statistics.median(sm) if sm else None),
+                "sm_mhz_min_under_load": min(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "samples_under_load": len(load),
+                "reasons": sorted(reasons)}
 
 
 def cpu_attention_sample(N, d, causal, heads, torch):
@@ -182,12 +187,12 @@ def run_ours(args, wl, wl_name):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
     launches0 = fa_b200.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
