@@ -165,7 +165,11 @@ int launch_fp32(const fa::Fp32Params& p, cudaStream_t st) {
 }
 
 int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, int B, int Hq, int Hkv, int Nq, int Nk,
-             int d, int dtype, float scale, int causal, const long long* s, cudaStream_t st) {
+             int d, int dtype, float scale, int causal, const long long* s, cudaStream_t st,
+             float* acc_o = nullptr, float* acc_lse = nullptr) {
+    const bool carry = acc_o != nullptr;
+    if (carry && (!acc_lse || dtype == FA_DTYPE_F32)) return fail(FA_ERR_INVALID_ARGUMENT, "carry mode needs acc_lse and a 16-bit dtype");
+    if (carry) O = acc_o;   // only used for the null / alignment checks below
     if (!Q || !K || !V || !O) return fail(FA_ERR_INVALID_ARGUMENT, "null tensor pointer");
     if (B <= 0 || Hq <= 0 || Hkv <= 0 || Nq <= 0 || Nk <= 0 || d <= 0)
         return fail(FA_ERR_INVALID_ARGUMENT, "non-positive size (B=%d Hq=%d Hkv=%d Nq=%d Nk=%d d=%d)", B, Hq, Hkv, Nq, Nk, d);
@@ -220,7 +224,7 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     if (int rc = make_tile_map(&tv, V, dtype, B, Hkv, Nk, d, s[6], s[7], s[8])) return rc;
 
     fa::FwdParams p;
-    p.O = O; p.lse = lse; p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
+    p.O = O; p.lse = lse; p.acc_o = acc_o; p.acc_lse = acc_lse; p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
     p.o_stride_b = s[9]; p.o_stride_h = s[10]; p.o_stride_n = s[11];
     p.scale = sc; p.scale_log2 = sc * 1.4426950408889634f;
     p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
@@ -267,6 +271,18 @@ int fa_fwd_strided(const void* Q, const void* K, const void* V, void* O, float* 
     g_err[0] = 0;
     if (!strides) return fail(FA_ERR_INVALID_ARGUMENT, "strides is null");
     return fwd_impl(Q, K, V, O, lse, B, Hq, Hkv, Nq, Nk, d, dtype, scale, causal, strides, (cudaStream_t)stream);
+}
+
+int fa_fwd_carry(const void* Q, const void* K, const void* V, float* acc_o, float* acc_lse, int B, int Hq, int Hkv,
+                 int Nq, int Nk, int d, int dtype, float scale, int causal, const long long* qkv_strides, void* stream) {
+    g_err[0] = 0;
+    if (!acc_o || !acc_lse) return fail(FA_ERR_INVALID_ARGUMENT, "acc_o / acc_lse is null");
+    long long s[12];
+    const long long qs[3] = {(long long)Hq * Nq * d, (long long)Nq * d, d};
+    const long long ks[3] = {(long long)Hkv * Nk * d, (long long)Nk * d, d};
+    for (int i = 0; i < 3; ++i) { s[i] = qs[i]; s[3 + i] = ks[i]; s[6 + i] = ks[i]; s[9 + i] = qs[i]; }
+    if (qkv_strides) for (int i = 0; i < 9; ++i) s[i] = qkv_strides[i];
+    return fwd_impl(Q, K, V, nullptr, nullptr, B, Hq, Hkv, Nq, Nk, d, dtype, scale, causal, s, (cudaStream_t)stream, acc_o, acc_lse);
 }
 
 int fa_mha_fwd_f32(const float* Q, const float* K, const float* V, float* O, int batchSize, int numHeads, int seqLen,

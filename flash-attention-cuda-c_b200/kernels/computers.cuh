@@ -296,38 +296,82 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             l_run += (s0.x + s0.y) + (s1.x + s1.y);
         }
 
-        // ---- epilogue: O / l -> global ----
+        // ---- epilogue ----
         const bool row_ok = row < p.Nq;
-        const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-        uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)w.b * p.o_stride_b + (long long)w.h * p.o_stride_h +
-                         (long long)row * p.o_stride_n;
-        if (n > 0) {
-            mbar_wait(o_full, (st + n - 1) & 1);
-            tc_fence_after();
+        const long long row_lin = ((long long)w.b * p.Hq + w.h) * p.Nq + row;
+        const float m_fin = (m_run == -INFINITY) ? 0.f : m_run;
+        const float lse_part = (l_run > 0.f) ? (m_fin * p.scale + logf(l_run)) : -INFINITY;
+        if (p.acc_o == nullptr) {
+            // plain mode: O / l -> global in the I/O dtype
+            const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+            uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)w.b * p.o_stride_b + (long long)w.h * p.o_stride_h +
+                             (long long)row * p.o_stride_n;
+            if (n > 0) {
+                mbar_wait(o_full, (st + n - 1) & 1);
+                tc_fence_after();
 #pragma unroll
-            for (int q = 0; q < D / 32; ++q) {
-                uint32_t o[32];
-                tmem_ld32(tO + 32u * q, o);
-                tc_wait_ld();
-                uint32_t h[16];
+                for (int q = 0; q < D / 32; ++q) {
+                    uint32_t o[32];
+                    tmem_ld32(tO + 32u * q, o);
+                    tc_wait_ld();
+                    uint32_t h[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    h[i] = pack16<DT>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
-                if (row_ok) {
+                    for (int i = 0; i < 16; ++i)
+                        h[i] = pack16<DT>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+                    if (row_ok) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        st_global_v4(orow + 32 * q + 8 * i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                        for (int i = 0; i < 4; ++i)
+                            st_global_v4(orow + 32 * q + 8 * i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(o_free);         // O columns may be overwritten by the next item's first P V
+            } else if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < D / 8; ++i) st_global_v4(orow + 8 * i, 0u, 0u, 0u, 0u);
+            }
+            if (p.lse != nullptr && row_ok) p.lse[row_lin] = lse_part;
+        } else {
+            // carry mode (ring-KV step): fold this call's partial result over its key range into the fp32 running
+            // (output, log-sum-exp) pair:  lse' = log(e^lse_acc + e^lse_part),  O' = O_acc e^(lse_acc-lse') + (O/l) e^(lse_part-lse')
+            float wa = 1.f, wp = 0.f, lse_new = -INFINITY;
+            if (row_ok) {
+                const float lse_acc = p.acc_lse[row_lin];
+                const float mx = fmaxf(lse_acc, lse_part);
+                lse_new = mx;
+                if (mx != -INFINITY) {
+                    const float ea = expf(lse_acc - mx), ep = expf(lse_part - mx);
+                    const float inv = 1.0f / (ea + ep);
+                    wa = ea * inv;
+                    wp = (l_run > 0.f) ? ep * inv / l_run : 0.f;
+                    lse_new = mx + logf(ea + ep);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(o_free);         // O columns may be overwritten by the next item's first P V
-        } else if (row_ok) {
+            if (n > 0) {
+                mbar_wait(o_full, (st + n - 1) & 1);
+                tc_fence_after();
+                float* arow = p.acc_o + row_lin * D;
 #pragma unroll
-            for (int i = 0; i < D / 8; ++i) st_global_v4(orow + 8 * i, 0u, 0u, 0u, 0u);
-        }
-        if (p.lse != nullptr && row_ok) {
-            const float m_safe = (m_run == -INFINITY) ? 0.f : m_run;
-            p.lse[((long long)w.b * p.Hq + w.h) * p.Nq + row] = (l_run > 0.f) ? (m_safe * p.scale + logf(l_run)) : -INFINITY;
+                for (int q = 0; q < D / 32; ++q) {
+                    uint32_t o[32];
+                    tmem_ld32(tO + 32u * q, o);
+                    tc_wait_ld();
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 a = ld_global_f4(arow + 32 * q + 4 * i);
+                            a.x = a.x * wa + __uint_as_float(o[4 * i + 0]) * wp;
+                            a.y = a.y * wa + __uint_as_float(o[4 * i + 1]) * wp;
+                            a.z = a.z * wa + __uint_as_float(o[4 * i + 2]) * wp;
+                            a.w = a.w * wa + __uint_as_float(o[4 * i + 3]) * wp;
+                            st_global_f4(arow + 32 * q + 4 * i, a);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(o_free);
+            }
+            if (row_ok && n > 0) p.acc_lse[row_lin] = lse_new;
         }
         st += n;
     }

@@ -45,6 +45,8 @@ constexpr int kEmuPairsPer8 = FA_EMU_PAIRS_PER_8;
 struct FwdParams {
     void* O;                 // output, same dtype as Q
     float* lse;              // optional [B, Hq, Nq] log-sum-exp (natural log), may be null
+    float* acc_o;            // carry mode (ring-KV steps): fp32 [B, Hq, Nq, d] running output, updated in place; O is not written
+    float* acc_lse;          // carry mode: fp32 [B, Hq, Nq] running log-sum-exp, updated in place
     int B, Hq, Hkv, Nq, Nk;
     long long o_stride_b, o_stride_h, o_stride_n;   // in elements; innermost (d) stride is 1
     float scale;             // softmax scale (1/sqrt(d) by default)

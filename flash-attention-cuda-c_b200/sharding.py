@@ -7,14 +7,16 @@ multi-device code at all; both modes are built on the single-GPU kernel behind t
 2. ring-KV — sequence-sharded long context.  Q/O stay resident on their rank; the K/V block of every rank
    travels once around the ring with point-to-point send/recv (NCCL over NVLink on GPUs; gloo in the CPU tests),
    posted before the local attention call so the transfer overlaps the MMAs.  Partial results over disjoint key
-   ranges are folded with the (O, log-sum-exp) carry of fa_merge_partial — the reference's running
-   (max, sum) recurrence (reference: kernels/utils.cuh:63-80) applied across ring steps instead of across tiles.
+   ranges are folded into an fp32 (O, log-sum-exp) carry inside the attention kernel's epilogue (fa_fwd_carry) —
+   the reference's running (max, sum) recurrence (reference: kernels/utils.cuh:63-80) applied across ring steps
+   instead of across tiles.
    Causal work is balanced with the zig-zag layout: the sequence is cut into 2P chunks and rank r owns chunks
    r and 2P-1-r, so every rank does the same amount of unmasked work at every step and fully masked block pairs
    are never launched.
 
-The ring driver takes the local attention and merge operators as arguments: on GPUs they default to the CUDA
-path (fa_b200); the CPU tests (gloo, world_size 2) pass CPU stand-ins to check schedule and plumbing.
+The ring driver takes the local "attend and fold into the carry" operator as an argument: on GPUs it defaults to
+the CUDA path (fa_b200.attention_forward_carry); the CPU tests (gloo, world_size 2) pass a CPU stand-in to check
+schedule and plumbing.
 """
 from __future__ import annotations
 
@@ -77,20 +79,16 @@ def _default_ops():
     import torch
     import fa_b200
 
-    def attn(q, k, v, causal):
-        return fa_b200.attention_forward(q, k, v, causal=causal, return_lse=True)
-
-    def merge(acc_o, acc_lse, o, lse):
-        fa_b200.merge_partial(acc_o, acc_lse, o, lse)
+    def step(q, k, v, causal, acc_o, acc_lse):
+        fa_b200.attention_forward_carry(q, k, v, acc_o, acc_lse, causal=causal)
 
     def finish(acc, like):
         return fa_b200.cast_out(acc, torch.empty(acc.shape, dtype=like.dtype, device=acc.device))
 
-    return attn, merge, finish
+    return step, finish
 
 
-def ring_attention(q, k, v, causal: bool = True, group=None,
-                   attn_fn: Optional[Callable] = None, merge_fn: Optional[Callable] = None,
+def ring_attention(q, k, v, causal: bool = True, group=None, step_fn: Optional[Callable] = None,
                    finish_fn: Optional[Callable] = None, return_lse: bool = False):
     """Sequence-sharded attention.  q [B,Hq,n,d], k/v [B,Hkv,n,d] are this rank's shard of the sequence
     (zig-zag layout when causal: [chunk r ; chunk 2P-1-r], contiguous otherwise).  Returns this rank's shard of O.
@@ -102,9 +100,9 @@ def ring_attention(q, k, v, causal: bool = True, group=None,
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     else:
         world, rank = 1, 0   # degenerate ring: one rank owns the whole sequence, no communication
-    if attn_fn is None or merge_fn is None or finish_fn is None:
-        d_attn, d_merge, d_finish = _default_ops()
-        attn_fn, merge_fn, finish_fn = attn_fn or d_attn, merge_fn or d_merge, finish_fn or d_finish
+    if step_fn is None or finish_fn is None:
+        d_step, d_finish = _default_ops()
+        step_fn, finish_fn = step_fn or d_step, finish_fn or d_finish
 
     B, Hq, n, d = q.shape
     half = n // 2
@@ -138,8 +136,7 @@ def ring_attention(q, k, v, causal: bool = True, group=None,
             ops = [dist.P2POp(dist.isend, kv, send_to, group), dist.P2POp(dist.irecv, nxt, recv_from, group)]
             reqs = dist.batch_isend_irecv(ops)
         for (_, _, qp, kp, c) in [e for e in sched if e[0] == s]:
-            o, lse = attn_fn(qparts[qp], part(kv[0], kp), part(kv[1], kp), c)
-            merge_fn(acc[qp][0], acc[qp][1], o, lse)
+            step_fn(qparts[qp], part(kv[0], kp), part(kv[1], kp), c, acc[qp][0], acc[qp][1])
         for r in reqs:
             r.wait()
         if s + 1 < world:

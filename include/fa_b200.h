@@ -87,6 +87,15 @@ int fa_fwd_host(const void* hQ, const void* hK, const void* hV, void* hO, float*
  */
 int fa_merge_partial(float* acc_o, float* acc_lse, const void* part_o, const float* part_lse,
                      long long rows, int d, int dtype, void* stream);
+/* fa_fwd_carry: one ring step with the merge fused into the attention kernel's epilogue: the partial result of
+ * attention(Q, K, V) over this call's key range is folded directly into the running pair (acc_o fp32 [B,Hq,Nq,d]
+ * contiguous, acc_lse fp32 [B,Hq,Nq]); no 16-bit O is written.  Start from acc_o = 0, acc_lse = -inf; finish with
+ * fa_cast_out.  16-bit dtypes only.  qkv_strides = {q_b,q_h,q_n, k_b,k_h,k_n, v_b,v_h,v_n} or NULL for contiguous.
+ * This is the "carry-in / carry-out (O, m, l)" kernel mode the reference's intended signature hinted at with its
+ * L / M pointers (reference: kernels/FlashAttention.cuh:21,36,50; archive/archive.cu:34-42). */
+int fa_fwd_carry(const void* Q, const void* K, const void* V, float* acc_o, float* acc_lse,
+                 int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype, float scale, int causal,
+                 const long long* qkv_strides, void* stream);
 /* fa_cast_out: fp32 accumulator -> 16-bit output tensor (n elements, n even). */
 int fa_cast_out(const float* src, void* dst, long long n, int dtype, void* stream);
 

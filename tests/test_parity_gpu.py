@@ -223,6 +223,30 @@ def test_merge_partial_equals_full_attention():
     assert np.abs(out16.float().cpu().numpy() - o_ref).max() <= TOL16
 
 
+def test_carry_mode_equals_full_attention():
+    # fa_fwd_carry: the merge fused into the kernel epilogue, over strided key slices, causal last block included
+    q, k, v = _inputs(2, 4, 2, 384, 1024, 128, torch.bfloat16, seed=13)
+    qc, kc, vc = q.cuda(), k.cuda(), v.cuda()
+    for causal in (False, True):
+        acc_o = torch.zeros(2, 4, 384, 128, device="cuda")
+        acc_l = torch.full((2, 4, 384), float("-inf"), device="cuda")
+        bounds = [0, 256, 640, 1024]
+        for i, (s, e) in enumerate(zip(bounds[:-1], bounds[1:])):
+            last = i == len(bounds) - 2
+            # only the last key block (which ends at Nk) carries the bottom-right aligned causal mask
+            fa_b200.attention_forward_carry(qc, kc[:, :, s:e], vc[:, :, s:e], acc_o, acc_l, causal=causal and last)
+        if causal:   # reference: keys < 640 fully visible, keys 640.. causal with offset (1024-640) - 384 = 0
+            kk = k.float().numpy(); vv = v.float().numpy(); qq = q.float().numpy()
+            o1, l1 = oracle.attention_fwd(qq, kk[:, :, :640], vv[:, :, :640], return_lse=True)
+            o2, l2 = oracle.attention_fwd(qq, kk[:, :, 640:], vv[:, :, 640:], causal=True, return_lse=True)
+            lse_ref = np.logaddexp(l1, l2)
+            o_ref = o1 * np.exp(l1 - lse_ref)[..., None] + o2 * np.exp(l2 - lse_ref)[..., None]
+        else:
+            o_ref, lse_ref = oracle.attention_fwd(q.float().numpy(), k.float().numpy(), v.float().numpy(), return_lse=True)
+        assert np.abs(acc_o.cpu().numpy() - o_ref).max() <= TOL16
+        np.testing.assert_allclose(acc_l.cpu().numpy(), lse_ref, atol=2e-3)
+
+
 # ---- full-size properties (BASELINE.json configs[2]: B=8 H=32 N=8192 d=128 causal bf16) ------------------
 def test_config3_full_size_properties():
     B, H, N, d = 8, 32, 8192, 128

@@ -54,12 +54,10 @@ def test_ring_schedule_covers_exactly_the_causal_block_pairs(world):
     assert max(work) == min(work), f"zig-zag must balance causal work: {work}"
 
 
-def _np_attn(q, k, v, causal):
+def _cpu_step(q, k, v, causal, acc_o, acc_lse):
+    """CPU stand-in for fa_fwd_carry: oracle attention over this key range, folded into the running (O, LSE) pair."""
     o, lse = oracle.attention_fwd(q.numpy(), k.numpy(), v.numpy(), causal=causal, return_lse=True)
-    return torch.from_numpy(o), torch.from_numpy(lse)
-
-
-def _np_merge(acc_o, acc_lse, o, lse):   # the carry fa_merge_partial implements, restated with torch on CPU
+    o, lse = torch.from_numpy(o), torch.from_numpy(lse)
     new = torch.logaddexp(acc_lse, lse)
     wa = torch.exp(acc_lse - new).nan_to_num(0.0)
     wb = torch.exp(lse - new).nan_to_num(0.0)
@@ -80,7 +78,7 @@ def _worker(rank, world, port, causal, shape, ret):
             ql, kl, vl = (sharding.zigzag_split(t, world, rank) for t in (q, k, v))
         else:
             ql, kl, vl = (t.chunk(world, dim=2)[rank].contiguous() for t in (q, k, v))
-        o, lse = sharding.ring_attention(ql, kl, vl, causal=causal, attn_fn=_np_attn, merge_fn=_np_merge,
+        o, lse = sharding.ring_attention(ql, kl, vl, causal=causal, step_fn=_cpu_step,
                                          finish_fn=lambda acc, like: acc.to(like.dtype), return_lse=True)
         outs = [torch.empty_like(o) for _ in range(world)]
         dist.all_gather(outs, o)
