@@ -18,7 +18,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libfa_b200.so")
+LIB_PATH = os.environ.get("FA_B200_LIB") or os.path.join(_HERE, "libfa_b200.so")   # env override: tuning builds only
 SOURCES = [os.path.join(_HERE, "kernels", f) for f in
            ("FlashAttention.cu", "FlashAttention.cuh", "loaders.cuh", "computers.cuh", "utils.cuh")]
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
