@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-line
 
 FA_DTYPE_F32, FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1, 2
 EXPORTS = ["fa_fwd", "fa_fwd_strided", "fa_fwd_carry", "fa_mha_fwd_f32", "fa_fwd_host", "fa_merge_partial", "fa_cast_out",
-           "fa_device_info", "fa_block_q", "fa_block_kv", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
+           "fa_set_sm_reserve", "fa_device_info", "fa_block_q", "fa_block_kv", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
 
 _lib = None
 
@@ -65,6 +65,7 @@ def lib() -> ctypes.CDLL:
         L.fa_merge_partial.argtypes = [vp, vp, vp, vp, ll, ip, ip, vp]
         L.fa_cast_out.argtypes = [vp, vp, ll, ip, vp]
         L.fa_device_info.argtypes = [ip, vp]
+        L.fa_set_sm_reserve.argtypes = [ip]
         for name in ("fa_block_q", "fa_block_kv", "fa_num_cta"):
             getattr(L, name).argtypes = [ip, ip]
         for name in EXPORTS:
@@ -180,6 +181,11 @@ def attention_forward_carry(q, k, v, acc_o, acc_lse, causal=False, scale=None):
                                 B, Hq, Hkv, Nq, Nk, d, _dtype_code(q), float(scale) if scale else 0.0,
                                 int(bool(causal)), strides, _stream_ptr(q))
     _check(rc, "fa_fwd_carry")
+
+
+def set_sm_reserve(sms: int):
+    """Leave `sms` SMs free of attention CTAs (for a concurrent NCCL send/recv kernel)."""
+    _check(lib().fa_set_sm_reserve(int(sms)), "fa_set_sm_reserve")
 
 
 def cast_out(src_f32, dst16):

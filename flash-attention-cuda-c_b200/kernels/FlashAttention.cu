@@ -19,6 +19,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_sm_reserve{0};       // fa_set_sm_reserve: SMs the persistent kernel leaves unoccupied
 unsigned long long* g_prof = nullptr;   // device buffer of phase counters; only set by fa_debug_set_profile_buffer
 
 int fail(int code, const char* fmt, ...) {
@@ -139,7 +140,9 @@ int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
     int sm_count = 0;
     p.sched_counter = next_counter(st, &sm_count);
     if (!p.sched_counter) return fail(FA_ERR_CUDA, "work-item counter allocation failed");
-    const int grid = p.total_items < sm_count ? p.total_items : sm_count;   // persistent: one CTA per SM
+    int max_ctas = sm_count - g_sm_reserve.load();      // SMs left free for a concurrent communication kernel
+    if (max_ctas < 1) max_ctas = 1;
+    const int grid = p.total_items < max_ctas ? p.total_items : max_ctas;   // persistent: one CTA per SM
     kern<<<grid, fa::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
     g_launches.fetch_add(1);
     FA_CUDA(cudaGetLastError());
@@ -255,6 +258,12 @@ extern "C" {
 
 // Debug hook (not in include/fa_b200.h): phase-counter buffer for FA_PHASE_PROFILE builds, 16 x u64 on the device.
 void fa_debug_set_profile_buffer(void* dev_ptr) { g_prof = (unsigned long long*)dev_ptr; }
+
+int fa_set_sm_reserve(int sms) {
+    if (sms < 0) return fail(FA_ERR_INVALID_ARGUMENT, "sms must be >= 0");
+    g_sm_reserve.store(sms);
+    return FA_OK;
+}
 
 const char* fa_last_error(void) { return g_err; }
 long long fa_launch_count(void) { return g_launches.load(); }

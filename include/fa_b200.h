@@ -113,6 +113,11 @@ int fa_block_kv(int d, int dtype);
 /* Replaces getNumCta (reference: helpers.hpp:33-36): CTAs along the query axis; ragged sizes round up, no assert. */
 int fa_num_cta(int q_dim, int q_block_size);
 
+/* fa_set_sm_reserve: the persistent attention kernel normally occupies every SM (one CTA per SM, all of its registers
+ * and shared memory).  A ring step overlaps it with an NCCL send/recv kernel that needs a few SMs of its own; reserving
+ * `sms` SMs (process-wide, default 0) lets that kernel run beside the MMAs instead of behind them. */
+int fa_set_sm_reserve(int sms);
+
 /* ---- diagnostics -------------------------------------------------------------------------------------------*/
 const char* fa_last_error(void);          /* thread-local text of the last failure, "" if none */
 long long fa_launch_count(void);          /* kernels this library has launched since load (bench: gpu_launches) */
