@@ -5,8 +5,14 @@ multi-device code at all; both modes are built on the single-GPU kernel behind t
    B*Hkv independent units (each unit carries its Hq/Hkv query heads, so K/V are never duplicated).
 
 2. ring-KV — sequence-sharded long context.  Q/O stay resident on their rank; the K/V block of every rank
-   travels once around the ring with point-to-point send/recv (NCCL over NVLink on GPUs; gloo in the CPU tests),
-   posted before the local attention call so the transfer overlaps the MMAs.  Partial results over disjoint key
+   travels once around the ring, one hop per step, overlapped with the MMAs of the current step.  Two transports:
+     "p2p"   point-to-point send/recv (NCCL over NVLink on GPUs; gloo in the CPU tests), posted before the local
+             attention calls.  NCCL moves the data with SM kernels, so the persistent attention kernel leaves a few
+             SMs free for it (fa_set_sm_reserve); at 8 ranks the hop bandwidth (~77 GB/s measured) becomes the limit.
+     "peer"  the K/V double buffer lives in symmetric memory (torch.distributed._symmetric_memory: every rank maps
+             every peer's buffer over NVLink); each rank PULLS its predecessor's block with a plain device copy on a
+             side stream (~690 GB/s measured, no SMs beyond a one-CTA barrier kernel per step) and device-side
+             barriers order the hops.  Default on GPUs ("auto") when the rendezvous succeeds.  Partial results over disjoint key
    ranges are folded into an fp32 (O, log-sum-exp) carry inside the attention kernel's epilogue (fa_fwd_carry) —
    the reference's running (max, sum) recurrence (reference: kernels/utils.cuh:63-80) applied across ring steps
    instead of across tiles.
@@ -88,8 +94,50 @@ def _default_ops():
     return step, finish
 
 
+class _PeerRing:
+    """K/V double buffer in symmetric memory + the copy stream the hops run on.  One per (shape, dtype, group)."""
+
+    def __init__(self, kv_shape, dtype, device, group):
+        import math
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.kv_shape = tuple(kv_shape)
+        self.dtype = dtype
+        self.numel = math.prod(self.kv_shape)
+        self.buf = symm.empty((2, self.numel), dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.copy_stream = torch.cuda.Stream(device=device)
+
+    def slot(self, i):
+        return self.buf[i].view(self.kv_shape)
+
+    def peer_slot(self, rank, i):
+        return self.hdl.get_buffer(rank, self.kv_shape, self.dtype, i * self.numel)
+
+
+_PEER_RINGS = {}
+_PEER_DISABLED = [False]
+
+
+def _peer_ring(kv_shape, dtype, device, group):
+    """Cached symmetric-memory ring for this shape, or None when symmetric memory is unavailable."""
+    if _PEER_DISABLED[0]:
+        return None
+    key = (tuple(kv_shape), dtype, str(device), id(group))
+    if key not in _PEER_RINGS:
+        try:
+            _PEER_RINGS[key] = _PeerRing(kv_shape, dtype, device, group)
+        except Exception as ex:    # rendezvous is collective: it fails (or works) on every rank alike
+            import warnings
+            warnings.warn(f"symmetric-memory ring unavailable ({ex}); using point-to-point send/recv")
+            _PEER_DISABLED[0] = True
+            return None
+    return _PEER_RINGS[key]
+
+
 def ring_attention(q, k, v, causal: bool = True, group=None, step_fn: Optional[Callable] = None,
-                   finish_fn: Optional[Callable] = None, return_lse: bool = False):
+                   finish_fn: Optional[Callable] = None, return_lse: bool = False, transport: str = "auto"):
     """Sequence-sharded attention.  q [B,Hq,n,d], k/v [B,Hkv,n,d] are this rank's shard of the sequence
     (zig-zag layout when causal: [chunk r ; chunk 2P-1-r], contiguous otherwise).  Returns this rank's shard of O.
     One send + one recv of the packed K/V block per step, none on the last step."""
@@ -108,9 +156,11 @@ def ring_attention(q, k, v, causal: bool = True, group=None, step_fn: Optional[C
     half = n // 2
     if causal and n % 2:
         raise ValueError("causal ring needs an even local length (two zig-zag chunks)")
-    # K and V travel as one buffer: a single send/recv pair per hop
-    kv = torch.stack([k, v]).contiguous()
-    nxt = torch.empty_like(kv) if world > 1 else None
+    ring = None
+    if world > 1 and q.is_cuda and transport in ("auto", "peer"):
+        ring = _peer_ring((2,) + tuple(k.shape), k.dtype, k.device, group)
+        if ring is None and transport == "peer":
+            raise RuntimeError("transport='peer' requested but symmetric memory is unavailable")
 
     def part(t, which):          # rows of the local sequence axis (dim -2); slices stay strided views
         if which == "ab":
@@ -127,20 +177,52 @@ def ring_attention(q, k, v, causal: bool = True, group=None, step_fn: Optional[C
         qparts = {"ab": q}
 
     sched = ring_schedule(world, rank, causal)
-    send_to, recv_from = (rank + 1) % world, (rank - 1) % world
-    if group is not None:
-        send_to, recv_from = dist.get_global_rank(group, send_to), dist.get_global_rank(group, recv_from)
-    for s in range(world):
-        reqs = []
-        if s + 1 < world:   # post the hop for the NEXT step first: it overlaps the attention calls below
-            ops = [dist.P2POp(dist.isend, kv, send_to, group), dist.P2POp(dist.irecv, nxt, recv_from, group)]
-            reqs = dist.batch_isend_irecv(ops)
+
+    def compute(s, kv):
         for (_, _, qp, kp, c) in [e for e in sched if e[0] == s]:
             step_fn(qparts[qp], part(kv[0], kp), part(kv[1], kp), c, acc[qp][0], acc[qp][1])
-        for r in reqs:
-            r.wait()
-        if s + 1 < world:
-            kv, nxt = nxt, kv
+
+    if ring is not None:
+        # ---- "peer": pull the predecessor's block out of its symmetric-memory slot on a side stream ----
+        prev = (rank - 1) % world
+        cur = torch.cuda.current_stream(q.device)
+        ring.hdl.barrier(channel=0)                   # every rank has finished with the previous call's slots
+        ring.slot(0)[0].copy_(k)
+        ring.slot(0)[1].copy_(v)
+        ring.hdl.barrier(channel=0)                   # slot 0 of every rank holds its own block
+        ev_prev = cur.record_event()
+        ev_pull = None
+        for s in range(world):
+            if s + 1 < world:
+                ring.copy_stream.wait_event(ev_prev)  # s = 0: slots filled; s > 0: my step s-1 no longer reads slot (s+1)%2
+                with torch.cuda.stream(ring.copy_stream):
+                    if s > 0:
+                        ring.hdl.barrier(channel=1)   # all ranks: hop s-1 landed and step s-1 computed
+                    ring.slot((s + 1) & 1).copy_(ring.peer_slot(prev, s & 1))
+                    ev_next = ring.copy_stream.record_event()
+            if ev_pull is not None:
+                cur.wait_event(ev_pull)               # this step's block has landed
+            compute(s, ring.slot(s & 1))
+            ev_prev = cur.record_event()
+            if s + 1 < world:
+                ev_pull = ev_next
+    else:
+        # ---- "p2p": K and V travel as one buffer, a single send/recv pair per hop ----
+        kv = torch.stack([k, v]).contiguous()
+        nxt = torch.empty_like(kv) if world > 1 else None
+        send_to, recv_from = (rank + 1) % world, (rank - 1) % world
+        if group is not None:
+            send_to, recv_from = dist.get_global_rank(group, send_to), dist.get_global_rank(group, recv_from)
+        for s in range(world):
+            reqs = []
+            if s + 1 < world:   # post the hop for the NEXT step first: it overlaps the attention calls below
+                ops = [dist.P2POp(dist.isend, kv, send_to, group), dist.P2POp(dist.irecv, nxt, recv_from, group)]
+                reqs = dist.batch_isend_irecv(ops)
+            compute(s, kv)
+            for r in reqs:
+                r.wait()
+            if s + 1 < world:
+                kv, nxt = nxt, kv
     if causal:
         o = torch.cat([finish_fn(acc["a"][0], q), finish_fn(acc["b"][0], q)], dim=2)
         lse = torch.cat([acc["a"][1], acc["b"][1]], dim=2)

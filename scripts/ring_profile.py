@@ -9,17 +9,18 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 reserve = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+transport = sys.argv[2] if len(sys.argv) > 2 else "auto"
 fa_b200.set_sm_reserve(reserve)
 B, H, N, d = 1, 8, 131072, 128
 n = N // world
 q, k, v = (torch.randn(B, H, n, d, device="cuda").to(torch.bfloat16) for _ in range(3))
-for _ in range(3): sharding.ring_attention(q, k, v, causal=True)
+for _ in range(3): sharding.ring_attention(q, k, v, causal=True, transport=transport)
 torch.cuda.synchronize(); dist.barrier()
 ms = []
 for _ in range(5):
     torch.cuda.synchronize(); dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter(); a.record(); sharding.ring_attention(q, k, v, causal=True); b.record(); t_cpu = time.perf_counter() - t0
+    t0 = time.perf_counter(); a.record(); sharding.ring_attention(q, k, v, causal=True, transport=transport); b.record(); t_cpu = time.perf_counter() - t0
     torch.cuda.synchronize(); ms.append((a.elapsed_time(b), t_cpu * 1e3))
 # compute-only: the same calls without communication
 half = n // 2
@@ -45,6 +46,6 @@ hop = a.elapsed_time(b)
 if rank == 0:
     F = 4.0 * B * H * N * N * d / 2
     best = min(m for m, _ in ms)
-    print(f"world {world} reserve {reserve}: ring GPU ms {[round(m, 2) for m, _ in ms]} cpu-side ms {[round(c, 2) for _, c in ms]} -> {F / best / 1e9:.0f} TFLOP/s; "
+    print(f"world {world} reserve {reserve} transport {transport}: ring GPU ms {[round(m, 2) for m, _ in ms]} cpu-side ms {[round(c, 2) for _, c in ms]} -> {F / best / 1e9:.0f} TFLOP/s; "
           f"compute-only (same calls, no comm) {comp:.2f} ms; one hop of {kv.numel() * 2 / 2**20:.0f} MiB {hop:.2f} ms ({kv.numel() * 2 / hop / 1e6:.0f} GB/s)", flush=True)
 dist.destroy_process_group()
