@@ -160,6 +160,8 @@ def run_ours(args, wl, wl_name):
     if ring:
         import sharding
         N = N // world           # this rank's rows (two zig-zag chunks of N/(2*world))
+        if world > 1:
+            fa_b200.set_sm_reserve(4)   # room for the one-CTA barrier kernels (peer transport) / NCCL kernels (p2p)
     tdt = {"bf16": torch.bfloat16, "fp16": torch.float16}[dtype]
     dev = torch.device("cuda", local)
     g = torch.Generator(device=dev).manual_seed(rank)
@@ -272,7 +274,9 @@ def run_ours(args, wl, wl_name):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if wl_name in STRONG else "weak", "vs_baseline": None,
                 "dtype": dtype, "data": "synthetic",
                 "config": {"workload": desc, "per_gpu": {"B": B, "Hq": Hq, "Hkv": Hkv, "N": N, "d": d, "causal": causal},
-                           "sharding": ("sequence-sharded ring-KV: K/V blocks rotate with NCCL send/recv, one hop per step, overlapped with the MMAs"
+                           "sharding": ("sequence-sharded ring-KV, zig-zag causal layout: one K/V hop per step overlapped with the MMAs; transport "
+                                        + ("symmetric-memory peer pull over NVLink (copy on a side stream), NCCL send/recv as fallback"
+                                           if (world > 1 and sharding._PEER_RINGS) else "NCCL send/recv")
                                         if ring else "(batch x head) units per rank, no data-path collective"),
                            "l2": ("working set %.2f GiB > 126 MB L2" % (alg_bytes / 2**30)) if flush is None else "L2 flushed (256 MiB write) between timed iterations",
                            "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
