@@ -5,7 +5,7 @@
 // per-tile-normalised softmax state.  Here the helpers are the raw sm_100a building blocks the
 // stages in loaders.cuh / computers.cuh are made of:
 //   * mbarrier (init / expect_tx / arrive / parity wait with a hang guard)
-//   * TMA bulk-tensor loads (cp.async.bulk.tensor.4d)
+//   * TMA bulk-tensor loads (cp.async.bulk.tensor.4d) with L2 eviction hints
 //   * tcgen05: TMEM alloc/dealloc, mma (SS and TS forms), commit, ld/st, fences
 //   * UMMA shared-memory / instruction descriptor builders
 //   * packed fp32x2 math, exp2, bf16/fp16 packing
@@ -62,9 +62,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -123,23 +120,6 @@ __device__ __forceinline__ void tma_load_4d_hint(const CUtensorMap* m, uint32_t 
         ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
           "l"(policy)
         : "memory");
-}
-// 4-D tiled store (shared -> global), bulk-group completion.
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_smem,
-                                             int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-        ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void tma_store_wait() {
-    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 // L2 eviction policies (same encodings createpolicy would return; used as cache hints)
 static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
@@ -250,14 +230,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
 
 // ------------------------------------------------------------------------------------------
 // math
@@ -283,15 +255,6 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
     asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
-    return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-    uint64_t ua, ub, ud;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
     float2 d;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
     return d;

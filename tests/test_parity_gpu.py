@@ -93,6 +93,36 @@ def test_16bit_gqa(hq, hkv):
     _check(*_inputs(2, hq, hkv, 384, 384, 128, torch.bfloat16, seed=hq), causal=True)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_16bit_random_shapes(seed):
+    # randomised sweep over batch, heads (GQA ratios), ragged Nq != Nk, head dim, dtype, causal, scale
+    rng = np.random.default_rng(1000 + seed)
+    hkv = int(rng.choice([1, 2, 3]))
+    hq = hkv * int(rng.choice([1, 2, 4]))
+    nq, nk = int(rng.integers(1, 700)), int(rng.integers(1, 900))
+    d = int(rng.choice([64, 128]))
+    dtype = [torch.bfloat16, torch.float16][int(rng.integers(0, 2))]
+    causal = bool(rng.integers(0, 2))
+    scale = None if rng.integers(0, 2) else float(rng.uniform(0.05, 0.3))
+    _check(*_inputs(int(rng.integers(1, 4)), hq, hkv, nq, nk, d, dtype, seed=seed), causal=causal, scale=scale)
+
+
+def test_concurrent_streams_do_not_share_work_counters():
+    # two persistent launches in flight on different streams must not steal each other's work items
+    q, k, v = _inputs(2, 8, 8, 1024, 1024, 128, torch.bfloat16, seed=21)
+    qc, kc, vc = q.cuda(), k.cuda(), v.cuda()
+    ref = fa_b200.attention_forward(qc, kc, vc, causal=True)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(6):
+        for st in (s1, s2):
+            with torch.cuda.stream(st):
+                outs.append(fa_b200.attention_forward(qc, kc, vc, causal=True))
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, ref) for o in outs)
+
+
 def test_16bit_long_rows_trigger_rescale():
     # growing score magnitude along the key axis forces the lazy O rescale path (max grows by > 2^8 repeatedly)
     q, k, v = _inputs(1, 2, 2, 256, 2048, 128, torch.bfloat16, seed=11)
