@@ -65,6 +65,7 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(bar0 + 8 * (L::kBarSchedFull + t), 1);
             mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 1 + kSoftmaxWarps);   // MMA warp + every softmax warp
         }
+        mbar_init(bar0 + 8 * L::kBarSFree, 128);
         fence_mbar_init();
     } else if (warp == kLoadWarp && lane == 0) {
         tma_prefetch_desc(&tmQ);

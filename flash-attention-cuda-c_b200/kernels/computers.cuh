@@ -15,23 +15,47 @@
 // Normalisation by 1/l is deferred to the epilogue (the reference normalises every tile,
 // utils.cuh:79-80).  O is rescaled lazily: only when a row's max grew by more than 2^8 since the max
 // in use (then O *= exp2((m_used - m')c) through a tcgen05.ld / tcgen05.st round trip).
-// P overwrites the first 64 columns of its own S tile (two 16-bit values per 32-bit column); the
-// tensor pipe executes MMAs in issue order, so "P_t V_j" followed by "Q_t K_{j+1}^T -> S_t" is safe.
+// TMEM map (512 columns, kSharedS = true, the default):  S 0..127 | P_0 128..191 | P_1 192..255 | O_0 256..383 | O_1 384..511.
+// ONE score buffer is shared by both query tiles: a tile's softmax warpgroup copies its S row into registers
+// within ~100 clk of the MMA retiring and hands the buffer back (s_free), so the buffer is free long before the
+// tensor pipe needs it again; P_t (two 16-bit values per 32-bit column) has columns of its own.  That removes the
+// S/P aliasing of the first design (P_t over the head of S_t), under which "Q_t K_{j+1}^T" had to queue behind
+// "P_t V_j" and the tensor pipe idled for a third of every step: now the next score tile of a query tile is
+// computed while its softmax warpgroup is still exponentiating the current one, and the warpgroups never wait for S.
+// kSharedS = false keeps the aliased layout (S_t at 128t, P_t over its first 64 columns) for comparison builds.
 #pragma once
 
 #include "loaders.cuh"
 
 namespace fa {
 
+#ifndef FA_SHARED_S
+#define FA_SHARED_S 1
+#endif
+constexpr bool kSharedS = FA_SHARED_S != 0;
+#ifndef FA_MMA_ORDER
+#define FA_MMA_ORDER 0
+#endif
+#ifndef FA_PFREE_WAIT
+#define FA_PFREE_WAIT 1
+#endif
+constexpr int kPFreeWait = FA_PFREE_WAIT; // where the softmax pass checks that P_t V_{j-1} retired: 0 = before the exponentials, 1 = before the first P store, 2 = after the first quarter
+constexpr int kMmaOrder = FA_MMA_ORDER;   // shared-S issue order: 0 = Q_1K_{j+1} before the second half of P_0V_j, 1 = after it
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemS0 = 0;      // S tile t at columns 128*t
 constexpr uint32_t kTmemO0 = 256;    // O tile t at columns 256 + 128*t
+// S tile of query tile t: the one shared buffer at column 0, or (aliased layout) columns 128*t
+__host__ __device__ constexpr uint32_t tmem_s_col(int t) { return kSharedS ? 0u : 128u * uint32_t(t); }
+// P tile of query tile t: columns 128 + 64*t, or (aliased layout) the head of its own S tile
+__host__ __device__ constexpr uint32_t tmem_p_col(int t) { return kSharedS ? 128u + 64u * uint32_t(t) : 128u * uint32_t(t); }
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
 
 // ------------------------------------------------------------------------------------------------
 // MMA issuer: the whole warp walks the schedule (so that addresses and descriptors stay warp-uniform and live in
 // uniform registers); one elected lane issues each tcgen05.mma / tcgen05.commit.  Persistent: loops over the work
-// items the producer publishes.  Issue order per key tile j (t = query tile):  P_0V_j, Q_0K_{j+1}, P_1V_j, Q_1K_{j+1}
+// items the producer publishes.  Issue order per key tile j (t = query tile), shared-S layout:
+//     Q_0K_{j+1}, P_0V_j (keys 0..63), Q_1K_{j+1}, P_0V_j (keys 64..127), P_1V_j
+// Every Q K^T first waits until the consumer of the previous one has copied the shared S buffer out (s_free).
+// Aliased layout (kSharedS = false):  P_0V_j, Q_0K_{j+1}, P_1V_j, Q_1K_{j+1}.
 // ------------------------------------------------------------------------------------------------
 template <int D, int STAGES, int DT>
 __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p) {
@@ -46,36 +70,58 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
     // Descriptor templates with a zero start address; the 14-bit address field (bytes >> 4) is added per MMA.
     const uint64_t desc_k_major = umma_desc_sw128(0, 16, 1024);             // Q and K tiles (K-major)
     const uint64_t desc_mn_major = umma_desc_sw128(0, kHalfBytes, 1024);    // V tile (MN-major), 64-column halves 16 KiB apart
+    auto commit = [&](uint32_t b) { if (elect_one_sync()) tc_commit(b); };
+    FA_PROF_DECL(9);
+    int qk_seq = 0;           // Q K^T tiles issued so far (phase bookkeeping of the shared S buffer)
     auto issue_qk = [&](int t, uint32_t k_smem) {
+        if constexpr (kSharedS) {
+            // the softmax warpgroup that consumes the previous S tile has copied it into registers
+            if (qk_seq > 0) {
+                FA_PROF_MARK(3);
+                mbar_wait(bar(L::kBarSFree), (qk_seq - 1) & 1);
+                tc_fence_after();
+                FA_PROF_MARK(4 + t);     // waiting for the shared S buffer (by the query tile whose Q K^T is next)
+            }
+            ++qk_seq;
+        }
         const uint64_t a0 = desc_k_major + ((smem_base + L::kQOff + t * L::kQTileBytes) >> 4);
         const uint64_t b0 = desc_k_major + (k_smem >> 4);
-        const uint32_t d_tmem = tmem_base + kTmemS0 + 128u * t;
+        const uint32_t d_tmem = tmem_base + tmem_s_col(t);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-            // 16 halfs = 32 B inside the 128-B swizzle row; the second 64 columns live one half (16 KiB) further
-            const uint32_t off = ((ks / 4) * kHalfBytes + (ks % 4) * 32) >> 4;
-            if (elect_one_sync()) umma_ss(d_tmem, a0 + off, b0 + off, idesc_qk, ks > 0);
+            for (int ks = 0; ks < D / 16; ++ks) {
+                // 16 halfs = 32 B inside the 128-B swizzle row; the second 64 columns live one half (16 KiB) further
+                const uint32_t off = ((ks / 4) * kHalfBytes + (ks % 4) * 32) >> 4;
+                umma_ss(d_tmem, a0 + off, b0 + off, idesc_qk, ks > 0);
+            }
+            tc_commit(bar(L::kBarSFull + t));
         }
+        __syncwarp();
     };
     // P_t V_j in two halves of 4 k-steps (64 keys each): the first half can start while the softmax warpgroup is still
     // producing the second half of P.
     auto issue_pv_half = [&](int t, uint32_t v_smem, bool accumulate, int half) {
-        const uint32_t p_tmem = tmem_base + kTmemS0 + 128u * t;    // P aliases the head of S_t
+        const uint32_t p_tmem = tmem_base + tmem_p_col(t);
         const uint32_t d_tmem = tmem_base + kTmemO0 + 128u * t;
         const uint64_t b0 = desc_mn_major + (v_smem >> 4);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < kBlockN / 32; ++kk) {
-            const int ks = half * (kBlockN / 32) + kk;
-            // 16 key rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B
-            if (elect_one_sync()) umma_ts(d_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (accumulate || ks > 0) ? 1u : 0u);
+            for (int kk = 0; kk < kBlockN / 32; ++kk) {
+                const int ks = half * (kBlockN / 32) + kk;
+                // 16 key rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B
+                umma_ts(d_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (accumulate || ks > 0) ? 1u : 0u);
+            }
+            if (half == 1) tc_commit(bar(L::kBarOFull + t));
         }
+        __syncwarp();
     };
     auto slot_addr = [&](int it) { return smem_base + L::kKVOff + (it % STAGES) * L::kKVTileBytes; };
-    auto wait_full = [&](int it) { mbar_wait(bar(L::kBarKVFull + it % STAGES), (it / STAGES) & 1); };
-    auto commit = [&](uint32_t b) { if (elect_one_sync()) tc_commit(b); };
+    auto wait_full = [&](int it) {
+        mbar_wait(bar(L::kBarKVFull + it % STAGES), (it / STAGES) & 1);
+        tc_fence_after();
+    };
     auto release = [&](int it) { commit(bar(L::kBarKVEmpty + it % STAGES)); };
 
-    FA_PROF_DECL(4);
     int it0 = 0;              // ring position of this item's K_0  (K_j = it0 + 2j, V_j = it0 + 2j + 1)
     int kq = 0;               // items with work so far (Q loads consumed)
     int st0 = 0, st1 = 0;     // key tiles processed so far, per query tile (barrier phase bookkeeping)
@@ -87,63 +133,79 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
         const int n = w.n_kv;
         if (n <= 0) continue;
 
+        // wait for one half of P_t (softmax -> MMA) and multiply it with V_j; the first use of O_t in an item also
+        // waits until the previous item's epilogue has read O_t out of TMEM
+        auto pv_half = [&](int t, int j, int half) {
+            const uint32_t ph = ((t == 0 ? st0 : st1) + j) & 1;
+            const int ko_t = t == 0 ? ko0 : ko1;
+            if (half == 0 && j == 0 && ko_t > 0) mbar_wait(bar(L::kBarOFree + t), (ko_t - 1) & 1);
+            mbar_wait(bar(L::kBarPFull + 2 * t + half), ph);
+            tc_fence_after();
+            FA_PROF_MARK(t == 0 ? (half == 0 ? 2 : 6) : 7 + half);   // waiting for P
+            issue_pv_half(t, slot_addr(it0 + 2 * j + 1), j > 0, half);
+            FA_PROF_MARK(3);             // issue + bookkeeping
+        };
+
         mbar_wait(bar(L::kBarQFull), kq & 1);
         ++kq;
         wait_full(it0);
-        tc_fence_after();
         FA_PROF_MARK(0);                 // Q + K0 arrival
 #pragma unroll
         for (int t = 0; t < kTilesPerCta; ++t)
-            if (w.n_tile(t) > 0) {
-                issue_qk(t, slot_addr(it0));
-                commit(bar(L::kBarSFull + t));
-            }
+            if (w.n_tile(t) > 0) issue_qk(t, slot_addr(it0));
         if (n == 1) commit(bar(L::kBarQEmpty));      // that was the item's last use of the Q tiles
         release(it0);
+        FA_PROF_MARK(3);
 
         for (int j = 0; j < n; ++j) {
             const int it_v = it0 + 2 * j + 1, it_k = it0 + 2 * j + 2;
             const bool has_next = j + 1 < n;
-            FA_PROF_MARK(3);             // issue + bookkeeping
-            wait_full(it_v);
-            FA_PROF_MARK(1);             // waiting for K/V tiles
-            bool k_ready = false;
-#pragma unroll
-            for (int t = 0; t < kTilesPerCta; ++t) {
-                if (j < w.n_tile(t)) {
-                    const uint32_t ph = ((t == 0 ? st0 : st1) + j) & 1;
-                    const int ko_t = t == 0 ? ko0 : ko1;
-                    // the previous item's epilogue must have read O out of TMEM before this item overwrites it
-                    if (j == 0 && ko_t > 0) mbar_wait(bar(L::kBarOFree + t), (ko_t - 1) & 1);
-                    mbar_wait(bar(L::kBarPFull + 2 * t), ph);
-                    tc_fence_after();
-                    FA_PROF_MARK(2);     // waiting for P
-                    issue_pv_half(t, slot_addr(it_v), j > 0, 0);
+            if constexpr (kSharedS) {
+                if (has_next) wait_full(it_k);
+                FA_PROF_MARK(1);         // waiting for K/V tiles
+                if (j + 1 < w.n_tile0) issue_qk(0, slot_addr(it_k));
+                FA_PROF_MARK(3);
+                wait_full(it_v);
+                FA_PROF_MARK(1);
+                if (j < w.n_tile0) pv_half(0, j, 0);
+                if constexpr (kMmaOrder == 0) {
+                    if (j + 1 < w.n_tile1) issue_qk(1, slot_addr(it_k));
                     FA_PROF_MARK(3);
-                    mbar_wait(bar(L::kBarPFull + 2 * t + 1), ph);
-                    tc_fence_after();
-                    FA_PROF_MARK(2);
-                    issue_pv_half(t, slot_addr(it_v), j > 0, 1);
-                    commit(bar(L::kBarOFull + t));
+                    if (j < w.n_tile0) pv_half(0, j, 1);
+                } else {
+                    if (j < w.n_tile0) pv_half(0, j, 1);
+                    if (j + 1 < w.n_tile1) issue_qk(1, slot_addr(it_k));
+                    FA_PROF_MARK(3);
                 }
-                if (j + 1 < w.n_tile(t)) {
-                    if (!k_ready) {
-                        FA_PROF_MARK(3);
-                        wait_full(it_k);
-                        tc_fence_after();
-                        FA_PROF_MARK(1);
-                        k_ready = true;
+                if (j < w.n_tile1) {
+                    pv_half(1, j, 0);
+                    pv_half(1, j, 1);
+                }
+            } else {
+                wait_full(it_v);
+                FA_PROF_MARK(1);
+                bool k_ready = false;
+#pragma unroll
+                for (int t = 0; t < kTilesPerCta; ++t) {
+                    if (j < w.n_tile(t)) {
+                        pv_half(t, j, 0);
+                        pv_half(t, j, 1);
                     }
-                    issue_qk(t, slot_addr(it_k));
-                    commit(bar(L::kBarSFull + t));
+                    if (j + 1 < w.n_tile(t)) {
+                        if (!k_ready) {
+                            wait_full(it_k);
+                            FA_PROF_MARK(1);
+                            k_ready = true;
+                        }
+                        issue_qk(t, slot_addr(it_k));
+                        FA_PROF_MARK(3);
+                    }
                 }
+                if (has_next && !k_ready) wait_full(it_k);     // (cannot happen: the busiest tile always needs K_{j+1})
             }
             if (j + 2 == n) commit(bar(L::kBarQEmpty));   // K_{n-1} was the last tile multiplied with Q
             release(it_v);
-            if (has_next) {
-                if (!k_ready) wait_full(it_k);             // (cannot happen: the busiest tile always needs K_{j+1})
-                release(it_k);
-            }
+            if (has_next) release(it_k);
         }
         st0 += w.n_tile0;
         st1 += w.n_tile1;
@@ -152,7 +214,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
         it0 += 2 * n;
     }
     FA_PROF_MARK(3);
-    if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 8, 4);
+    if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 8, 9);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -169,11 +231,13 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
     const uint32_t p_full1 = p_full0 + 8u;
     const uint32_t o_full = bar0 + 8u * (L::kBarOFull + t);
     const uint32_t o_free = bar0 + 8u * (L::kBarOFree + t);
+    const uint32_t s_free = bar0 + 8u * L::kBarSFree;
 
     const int warp_in_wg = (threadIdx.x / 32) & 3;
     const int lane = threadIdx.x & 31;
     const uint32_t lane_base = uint32_t(warp_in_wg * 32) << 16;
-    const uint32_t tS = tmem_base + lane_base + kTmemS0 + 128u * t;
+    const uint32_t tS = tmem_base + lane_base + tmem_s_col(t);
+    const uint32_t tP = tmem_base + lane_base + tmem_p_col(t);
     const uint32_t tO = tmem_base + lane_base + kTmemO0 + 128u * t;
     const float c = p.scale_log2;
 
@@ -201,6 +265,10 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
 #pragma unroll
             for (int q = 0; q < kBlockN / 32; ++q) tmem_ld32(tS + 32u * q, r + 32 * q);
             tc_wait_ld();
+            if constexpr (kSharedS) {
+                tc_fence_before();
+                mbar_arrive(s_free);     // the score row is in registers: the shared S buffer may be overwritten
+            }
             FA_PROF_MARK(1);             // tcgen05.ld of the score row
 
             const int kv0 = j * kBlockN;
@@ -272,11 +340,24 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                     pk[cc / 2 + 1] = pack16<DT>(x1.x, x1.y);
                 }
             };
+            // P_t has columns of its own: P_t V_{j-1} must have retired before they are overwritten (it was issued when
+            // the previous pass ended, so it almost always has)
+            auto wait_p_free = [&]() {
+                if constexpr (kSharedS) {
+                    if (j > 0) {
+                        mbar_wait(o_full, ph ^ 1);
+                        tc_fence_after();
+                    }
+                }
+            };
+            if constexpr (kPFreeWait == 0) wait_p_free();
             {
                 uint32_t pk[32];
                 exp_quarter(0, pk);
+                if constexpr (kPFreeWait == 2) wait_p_free();
                 exp_quarter(1, pk + 16);
-                tmem_st32(tS, pk);                 // keys 0..63 of P
+                if constexpr (kPFreeWait == 1) wait_p_free();
+                tmem_st32(tP, pk);                 // keys 0..63 of P
             }
             {
                 uint32_t pk[32];
@@ -285,7 +366,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 tc_fence_before();
                 mbar_arrive(p_full0);              // MMA may start P V on keys 0..63
                 exp_quarter(3, pk + 16);
-                tmem_st32(tS + 32u, pk);           // keys 64..127 of P
+                tmem_st32(tP + 32u, pk);           // keys 64..127 of P
             }
             FA_PROF_MARK(3);             // exp2 / pack / tcgen05.st issue
             tc_wait_st();

@@ -78,7 +78,8 @@ struct SmemLayout {
     static constexpr int kBarOFree = kBarOFull + 2;            // [2]    softmax -> MMA : epilogue has read O out of TMEM
     static constexpr int kBarSchedFull = kBarOFree + 2;        // [2]    TMA -> all     : next work item published
     static constexpr int kBarSchedEmpty = kBarSchedFull + 2;   // [2]    all -> TMA     : work item slot consumed
-    static constexpr int kNumBars = kBarSchedEmpty + 2;
+    static constexpr int kBarSFree = kBarSchedEmpty + 2;       //        softmax -> MMA : shared S buffer copied into registers
+    static constexpr int kNumBars = kBarSFree + 1;
     static constexpr int kSchedItemOff = kBarOff + kNumBars * 8;   // int[2]
     static constexpr int kTmemPtrOff = kSchedItemOff + 8;
     static constexpr int kBytes = kTmemPtrOff + 16;

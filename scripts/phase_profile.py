@@ -10,7 +10,7 @@ L.fa_debug_set_profile_buffer.argtypes = [ctypes.c_void_p]
 B, H, N, d, causal = [int(x) for x in (sys.argv[1:6] if len(sys.argv) > 5 else (8, 32, 8192, 128, 1))]
 q, k, v = (torch.randn(B, H, N, d, device="cuda").to(torch.bfloat16) for _ in range(3))
 fa_b200.attention_forward(q, k, v, causal=bool(causal)); torch.cuda.synchronize()
-prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+prof = torch.zeros(32, dtype=torch.int64, device="cuda")
 L.fa_debug_set_profile_buffer(prof.data_ptr())
 fa_b200.attention_forward(q, k, v, causal=bool(causal)); torch.cuda.synchronize()
 p = prof.cpu().tolist()
@@ -18,6 +18,7 @@ nq = (N + 255) // 256
 tiles = sum(min((N + 127) // 128, ((qb * 256 + 255) // 128 + 1)) if causal else (N + 127) // 128 for qb in range(nq)) * B * H   # kv iterations summed over CTAs
 names = ["wait_S", "ld_S", "mask_max_rescale", "exp_pack_st", "st_drain_arrive", "loop_misc"]
 sm = {n: p[i] / (8 * tiles) for i, n in enumerate(names)}      # 8 softmax warps per CTA report, per kv iteration
-mma = {n: p[8 + i] / tiles for i, n in enumerate(["prologue(per CTA, amortised)", "wait_KV", "wait_P(both tiles)", "issue"])}
+mma = {n: p[8 + i] / tiles for i, n in enumerate(["prologue(per CTA, amortised)", "wait_KV", "wait_P0_h0", "issue", "wait_S_free_for_QK0", "wait_S_free_for_QK1", "wait_P0_h1", "wait_P1_h0", "wait_P1_h1"])}
+sm = {k: round(x, 1) for k, x in sm.items()}; mma = {k: round(x, 1) for k, x in mma.items()}
 print(json.dumps({"lib": os.path.basename(fa_b200.LIB_PATH), "shape": [B, H, N, d, causal], "kv_iterations": tiles, "softmax_warp_cycles_per_kv_iteration": sm,
                   "softmax_total": sum(sm.values()), "mma_thread_cycles_per_kv_iteration": mma, "mma_total": sum(mma.values())}))
