@@ -31,9 +31,9 @@ namespace fa {
 // of one (batch, head), claimed from a global atomic counter (LPT order inside a head, (batch, head)-major overall).
 //   warps 0-3  softmax + correction + epilogue for query tile 0
 //   warps 4-7  softmax + correction + epilogue for query tile 1
-//   warp  8    MMA issuer (one thread)
-//   warp  9    TMA producer (one thread)
-//   warp 10    TMEM allocator
+//   warp  8    MMA issuer for query tile 0
+//   warp  9    TMA producer + scheduler (one thread)
+//   warp 10    TMEM allocator, then MMA issuer for query tile 1
 // ------------------------------------------------------------------------------------------------
 template <int D, int STAGES, int DT>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -48,13 +48,13 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int warp = threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
 
-    if (warp == kMmaWarp && lane == 0) {
+    if (warp == kMmaWarp0 && lane == 0) {
         const uint32_t bar0 = smem_base + L::kBarOff;
         mbar_init(bar0 + 8 * L::kBarQFull, 1);
-        mbar_init(bar0 + 8 * L::kBarQEmpty, 1);
+        mbar_init(bar0 + 8 * L::kBarQEmpty, 2);                     // both MMA issuers
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar0 + 8 * (L::kBarKVFull + s), 1);
-            mbar_init(bar0 + 8 * (L::kBarKVEmpty + s), 1);
+            mbar_init(bar0 + 8 * (L::kBarKVEmpty + s), 2);          // both MMA issuers
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar0 + 8 * (L::kBarSFull + t), 1);
@@ -63,9 +63,9 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(bar0 + 8 * (L::kBarOFull + t), 1);
             mbar_init(bar0 + 8 * (L::kBarOFree + t), 128);
             mbar_init(bar0 + 8 * (L::kBarSchedFull + t), 1);
-            mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 1 + kSoftmaxWarps);   // MMA warp + every softmax warp
+            mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 2 + kSoftmaxWarps);   // both MMA issuers + every softmax warp
+            mbar_init(bar0 + 8 * (L::kBarSFree + t), 128);
         }
-        mbar_init(bar0 + 8 * L::kBarSFree, 128);
         fence_mbar_init();
     } else if (warp == kLoadWarp && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -85,8 +85,10 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         softmaxWarpgroup<D, STAGES, DT>(smem_base, tmem_base, p, warp / 4);
     } else {
         reg_dec<kOtherRegs>();
-        if (warp == kMmaWarp) {
-            mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p);
+        if (warp == kMmaWarp0) {
+            mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 0);
+        } else if (warp == kMmaWarp1) {
+            mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 1);
         } else if (warp == kLoadWarp) {
             if (lane == 0) tmaLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, p);
         }

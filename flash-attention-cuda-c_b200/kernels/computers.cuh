@@ -33,14 +33,10 @@ namespace fa {
 #define FA_SHARED_S 1
 #endif
 constexpr bool kSharedS = FA_SHARED_S != 0;
-#ifndef FA_MMA_ORDER
-#define FA_MMA_ORDER 0
-#endif
 #ifndef FA_PFREE_WAIT
-#define FA_PFREE_WAIT 1
+#define FA_PFREE_WAIT 0
 #endif
 constexpr int kPFreeWait = FA_PFREE_WAIT; // where the softmax pass checks that P_t V_{j-1} retired: 0 = before the exponentials, 1 = before the first P store, 2 = after the first quarter
-constexpr int kMmaOrder = FA_MMA_ORDER;   // shared-S issue order: 0 = Q_1K_{j+1} before the second half of P_0V_j, 1 = after it
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemO0 = 256;    // O tile t at columns 256 + 128*t
 // S tile of query tile t: the one shared buffer at column 0, or (aliased layout) columns 128*t
@@ -50,15 +46,21 @@ __host__ __device__ constexpr uint32_t tmem_p_col(int t) { return kSharedS ? 128
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
 
 // ------------------------------------------------------------------------------------------------
-// MMA issuer: the whole warp walks the schedule (so that addresses and descriptors stay warp-uniform and live in
-// uniform registers); one elected lane issues each tcgen05.mma / tcgen05.commit.  Persistent: loops over the work
-// items the producer publishes.  Issue order per key tile j (t = query tile), shared-S layout:
-//     Q_0K_{j+1}, P_0V_j (keys 0..63), Q_1K_{j+1}, P_0V_j (keys 64..127), P_1V_j
-// Every Q K^T first waits until the consumer of the previous one has copied the shared S buffer out (s_free).
-// Aliased layout (kSharedS = false):  P_0V_j, Q_0K_{j+1}, P_1V_j, Q_1K_{j+1}.
+// MMA issuers: one warp per query tile t (warps kMmaWarp0 / kMmaWarp1).  The whole warp walks the schedule (so that
+// addresses and descriptors stay warp-uniform); one elected lane issues each batch of tcgen05.mma and its
+// tcgen05.commit.  Persistent: loops over the work items the producer publishes.
+// tcgen05.mma issue blocks while the tensor pipe's short queue is full, so an issuing warp runs in lock-step with the
+// pipe and every mbarrier wait it makes (~100 clk even when the barrier has already completed) is a bubble in the
+// pipe.  With two issuers the bubbles of one are filled by the MMAs of the other, and the order in which the two query
+// tiles' MMAs reach the pipe follows readiness instead of a fixed program order.
+// Per key tile j issuer t does, shared-S layout:   Q_tK_{j+1} (after the previous S tile has been copied out), P_tV_j
+//                                aliased layout:    P_tV_j, Q_tK_{j+1}
+// K/V slots and the Q tiles are handed back to the producer by BOTH issuers (barrier count 2): a tcgen05.commit when the
+// issuer multiplied with the tile, a plain arrive when it did not (causal blocks: the early query tile stops one key
+// tile sooner) — in both cases only after it has seen the slot full, which keeps the phases in step.
 // ------------------------------------------------------------------------------------------------
 template <int D, int STAGES, int DT>
-__device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p) {
+__device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p, const int t) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);   // tell the compiler it is warp-uniform
     using L = SmemLayout<D, STAGES>;
     constexpr uint32_t kFmt = (DT == kBF16) ? 1u : 0u;
@@ -70,151 +72,149 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
     // Descriptor templates with a zero start address; the 14-bit address field (bytes >> 4) is added per MMA.
     const uint64_t desc_k_major = umma_desc_sw128(0, 16, 1024);             // Q and K tiles (K-major)
     const uint64_t desc_mn_major = umma_desc_sw128(0, kHalfBytes, 1024);    // V tile (MN-major), 64-column halves 16 KiB apart
-    auto commit = [&](uint32_t b) { if (elect_one_sync()) tc_commit(b); };
-    FA_PROF_DECL(9);
-    int qk_seq = 0;           // Q K^T tiles issued so far (phase bookkeeping of the shared S buffer)
-    auto issue_qk = [&](int t, uint32_t k_smem) {
-        if constexpr (kSharedS) {
-            // the softmax warpgroup that consumes the previous S tile has copied it into registers
-            if (qk_seq > 0) {
-                FA_PROF_MARK(3);
-                mbar_wait(bar(L::kBarSFree), (qk_seq - 1) & 1);
-                tc_fence_after();
-                FA_PROF_MARK(4 + t);     // waiting for the shared S buffer (by the query tile whose Q K^T is next)
-            }
-            ++qk_seq;
-        }
-        const uint64_t a0 = desc_k_major + ((smem_base + L::kQOff + t * L::kQTileBytes) >> 4);
-        const uint64_t b0 = desc_k_major + (k_smem >> 4);
-        const uint32_t d_tmem = tmem_base + tmem_s_col(t);
+    const uint64_t q_desc = desc_k_major + ((smem_base + L::kQOff + t * L::kQTileBytes) >> 4);
+    const uint32_t s_tmem = tmem_base + tmem_s_col(t);
+    const uint32_t p_tmem = tmem_base + tmem_p_col(t);
+    const uint32_t o_tmem = tmem_base + kTmemO0 + 128u * t;
+    FA_PROF_DECL(6);
+
+    // S_t = Q_t K^T, then s_full[t]; `then_release` != 0: also hand the K slot / the Q tiles back (commit = arrive on completion)
+    auto issue_qk = [&](uint32_t k_smem, uint32_t release_bar, bool release_q) {
         if (elect_one_sync()) {
+            const uint64_t b0 = desc_k_major + (k_smem >> 4);
 #pragma unroll
             for (int ks = 0; ks < D / 16; ++ks) {
                 // 16 halfs = 32 B inside the 128-B swizzle row; the second 64 columns live one half (16 KiB) further
                 const uint32_t off = ((ks / 4) * kHalfBytes + (ks % 4) * 32) >> 4;
-                umma_ss(d_tmem, a0 + off, b0 + off, idesc_qk, ks > 0);
+                umma_ss(s_tmem, q_desc + off, b0 + off, idesc_qk, ks > 0);
             }
             tc_commit(bar(L::kBarSFull + t));
+            tc_commit(release_bar);
+            if (release_q) tc_commit(bar(L::kBarQEmpty));
         }
         __syncwarp();
     };
-    // P_t V_j in two halves of 4 k-steps (64 keys each): the first half can start while the softmax warpgroup is still
-    // producing the second half of P.
-    auto issue_pv_half = [&](int t, uint32_t v_smem, bool accumulate, int half) {
-        const uint32_t p_tmem = tmem_base + tmem_p_col(t);
-        const uint32_t d_tmem = tmem_base + kTmemO0 + 128u * t;
-        const uint64_t b0 = desc_mn_major + (v_smem >> 4);
+    // O_t (+)= P_t V_j in two halves of 4 k-steps (64 keys each): the first half can start while the softmax warpgroup
+    // is still producing the second half of P.  The second half ends with o_full[t] and the release of the V slot.
+    auto issue_pv_half = [&](uint32_t v_smem, bool accumulate, int half, uint32_t release_bar) {
         if (elect_one_sync()) {
+            const uint64_t b0 = desc_mn_major + (v_smem >> 4);
 #pragma unroll
             for (int kk = 0; kk < kBlockN / 32; ++kk) {
                 const int ks = half * (kBlockN / 32) + kk;
                 // 16 key rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B
-                umma_ts(d_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (accumulate || ks > 0) ? 1u : 0u);
+                umma_ts(o_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (accumulate || ks > 0) ? 1u : 0u);
             }
-            if (half == 1) tc_commit(bar(L::kBarOFull + t));
+            if (half == 1) {
+                tc_commit(bar(L::kBarOFull + t));
+                tc_commit(release_bar);
+            }
         }
         __syncwarp();
     };
     auto slot_addr = [&](int it) { return smem_base + L::kKVOff + (it % STAGES) * L::kKVTileBytes; };
+    auto empty_bar = [&](int it) { return bar(L::kBarKVEmpty + it % STAGES); };
     auto wait_full = [&](int it) {
         mbar_wait(bar(L::kBarKVFull + it % STAGES), (it / STAGES) & 1);
         tc_fence_after();
     };
-    auto release = [&](int it) { commit(bar(L::kBarKVEmpty + it % STAGES)); };
+    auto arrive = [&](uint32_t b) { if (elect_one_sync()) mbar_arrive(b); __syncwarp(); };
 
     int it0 = 0;              // ring position of this item's K_0  (K_j = it0 + 2j, V_j = it0 + 2j + 1)
     int kq = 0;               // items with work so far (Q loads consumed)
-    int st0 = 0, st1 = 0;     // key tiles processed so far, per query tile (barrier phase bookkeeping)
-    int ko0 = 0, ko1 = 0;     // items in which the query tile had work (O hand-back bookkeeping)
+    int st = 0;               // key tiles this issuer's query tile has processed so far (barrier phase bookkeeping)
+    int sq = 0;               // score-buffer steps so far (sum of n_kv over items; phase bookkeeping of s_free)
+    int ko = 0;               // items in which this issuer's query tile had work (O hand-back bookkeeping)
     for (int k = 0;; ++k) {
         const int item = fetch_item<D, STAGES>(smem_base, k);
         if (item < 0) break;
         const WorkItem w = decode_item(p, item);
         const int n = w.n_kv;
         if (n <= 0) continue;
+        const int nt = w.n_tile(t);
 
-        // wait for one half of P_t (softmax -> MMA) and multiply it with V_j; the first use of O_t in an item also
-        // waits until the previous item's epilogue has read O_t out of TMEM
-        auto pv_half = [&](int t, int j, int half) {
-            const uint32_t ph = ((t == 0 ? st0 : st1) + j) & 1;
-            const int ko_t = t == 0 ? ko0 : ko1;
-            if (half == 0 && j == 0 && ko_t > 0) mbar_wait(bar(L::kBarOFree + t), (ko_t - 1) & 1);
-            mbar_wait(bar(L::kBarPFull + 2 * t + half), ph);
+        // Shared S buffer: the CTA-wide order of the score tiles of an item is S_0(0), S_1(0), S_0(1), S_1(1), ... for ALL
+        // j < n; a tile a query tile does not take part in is a virtual step (its issuer passes the buffer on without
+        // an MMA), so both s_free barriers advance exactly n phases per item and every wait below is on the phase right
+        // after the one this warp waited on before.  S_t(j) may be written once its predecessor has been copied out.
+        auto wait_s_buffer = [&](int j) {
+            const int idx = (t == 0) ? sq + j - 1 : sq + j;     // predecessor: S_1(j-1) for tile 0, S_0(j) for tile 1
+            if (idx >= 0) {
+                mbar_wait(bar(L::kBarSFree + (1 - t)), idx & 1);
+                tc_fence_after();
+            }
+        };
+        auto virtual_qk = [&](int j) {
+            if constexpr (kSharedS) {
+                wait_s_buffer(j);
+                if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), 128);
+                __syncwarp();
+            }
+        };
+        auto pv = [&](int j) {
+            const uint32_t ph = (st + j) & 1;
+            // the previous item's epilogue must have read O_t out of TMEM before this item overwrites it
+            if (j == 0 && ko > 0) mbar_wait(bar(L::kBarOFree + t), (ko - 1) & 1);
+            FA_PROF_MARK(3);
+            mbar_wait(bar(L::kBarPFull + 2 * t), ph);
             tc_fence_after();
-            FA_PROF_MARK(t == 0 ? (half == 0 ? 2 : 6) : 7 + half);   // waiting for P
-            issue_pv_half(t, slot_addr(it0 + 2 * j + 1), j > 0, half);
+            FA_PROF_MARK(2);             // waiting for P
+            issue_pv_half(slot_addr(it0 + 2 * j + 1), j > 0, 0, 0);
             FA_PROF_MARK(3);             // issue + bookkeeping
+            mbar_wait(bar(L::kBarPFull + 2 * t + 1), ph);
+            tc_fence_after();
+            FA_PROF_MARK(2);
+            issue_pv_half(slot_addr(it0 + 2 * j + 1), j > 0, 1, empty_bar(it0 + 2 * j + 1));
+            FA_PROF_MARK(3);
+        };
+        auto qk = [&](int j) {
+            FA_PROF_MARK(3);
+            if constexpr (kSharedS) wait_s_buffer(j);
+            FA_PROF_MARK(4);             // waiting for the shared S buffer
+            issue_qk(slot_addr(it0 + 2 * j), empty_bar(it0 + 2 * j), j + 1 == nt);
+            FA_PROF_MARK(3);
         };
 
         mbar_wait(bar(L::kBarQFull), kq & 1);
         ++kq;
         wait_full(it0);
         FA_PROF_MARK(0);                 // Q + K0 arrival
-#pragma unroll
-        for (int t = 0; t < kTilesPerCta; ++t)
-            if (w.n_tile(t) > 0) issue_qk(t, slot_addr(it0));
-        if (n == 1) commit(bar(L::kBarQEmpty));      // that was the item's last use of the Q tiles
-        release(it0);
-        FA_PROF_MARK(3);
-
+        if (nt > 0) qk(0);
+        else {
+            virtual_qk(0);
+            arrive(empty_bar(it0));
+            arrive(bar(L::kBarQEmpty));
+        }
         for (int j = 0; j < n; ++j) {
             const int it_v = it0 + 2 * j + 1, it_k = it0 + 2 * j + 2;
             const bool has_next = j + 1 < n;
-            if constexpr (kSharedS) {
-                if (has_next) wait_full(it_k);
+            if constexpr (!kSharedS) {
+                wait_full(it_v);
                 FA_PROF_MARK(1);         // waiting for K/V tiles
-                if (j + 1 < w.n_tile0) issue_qk(0, slot_addr(it_k));
-                FA_PROF_MARK(3);
-                wait_full(it_v);
-                FA_PROF_MARK(1);
-                if (j < w.n_tile0) pv_half(0, j, 0);
-                if constexpr (kMmaOrder == 0) {
-                    if (j + 1 < w.n_tile1) issue_qk(1, slot_addr(it_k));
-                    FA_PROF_MARK(3);
-                    if (j < w.n_tile0) pv_half(0, j, 1);
-                } else {
-                    if (j < w.n_tile0) pv_half(0, j, 1);
-                    if (j + 1 < w.n_tile1) issue_qk(1, slot_addr(it_k));
-                    FA_PROF_MARK(3);
-                }
-                if (j < w.n_tile1) {
-                    pv_half(1, j, 0);
-                    pv_half(1, j, 1);
-                }
-            } else {
-                wait_full(it_v);
-                FA_PROF_MARK(1);
-                bool k_ready = false;
-#pragma unroll
-                for (int t = 0; t < kTilesPerCta; ++t) {
-                    if (j < w.n_tile(t)) {
-                        pv_half(t, j, 0);
-                        pv_half(t, j, 1);
-                    }
-                    if (j + 1 < w.n_tile(t)) {
-                        if (!k_ready) {
-                            wait_full(it_k);
-                            FA_PROF_MARK(1);
-                            k_ready = true;
-                        }
-                        issue_qk(t, slot_addr(it_k));
-                        FA_PROF_MARK(3);
-                    }
-                }
-                if (has_next && !k_ready) wait_full(it_k);     // (cannot happen: the busiest tile always needs K_{j+1})
+                if (j < nt) pv(j); else arrive(empty_bar(it_v));
             }
-            if (j + 2 == n) commit(bar(L::kBarQEmpty));   // K_{n-1} was the last tile multiplied with Q
-            release(it_v);
-            if (has_next) release(it_k);
+            if (has_next) {
+                wait_full(it_k);
+                FA_PROF_MARK(1);
+                if (j + 1 < nt) qk(j + 1);
+                else {
+                    virtual_qk(j + 1);
+                    arrive(empty_bar(it_k));
+                }
+            }
+            if constexpr (kSharedS) {
+                wait_full(it_v);
+                FA_PROF_MARK(1);
+                if (j < nt) pv(j); else arrive(empty_bar(it_v));
+            }
         }
-        st0 += w.n_tile0;
-        st1 += w.n_tile1;
-        ko0 += w.n_tile0 > 0 ? 1 : 0;
-        ko1 += w.n_tile1 > 0 ? 1 : 0;
+        st += nt;
+        sq += n;
+        ko += nt > 0 ? 1 : 0;
         it0 += 2 * n;
     }
     FA_PROF_MARK(3);
-    if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 8, 9);
+    if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 8 + 8 * t, 6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -231,7 +231,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
     const uint32_t p_full1 = p_full0 + 8u;
     const uint32_t o_full = bar0 + 8u * (L::kBarOFull + t);
     const uint32_t o_free = bar0 + 8u * (L::kBarOFree + t);
-    const uint32_t s_free = bar0 + 8u * L::kBarSFree;
+    const uint32_t s_free = bar0 + 8u * (L::kBarSFree + t);
 
     const int warp_in_wg = (threadIdx.x / 32) & 3;
     const int lane = threadIdx.x & 31;

@@ -29,9 +29,10 @@ constexpr int kHalfBytes = kBlockN * 128;   // 16 KiB: one half of a 128-row til
 
 // Warp roles (384 threads = 3 warpgroups)
 constexpr int kSoftmaxWarps = 8;   // warps 0-3: query tile 0, warps 4-7: query tile 1
-constexpr int kMmaWarp = 8;
+constexpr int kMmaWarp0 = 8;       // MMA issuer of query tile 0
 constexpr int kLoadWarp = 9;
-constexpr int kTmemWarp = 10;
+constexpr int kMmaWarp1 = 10;      // MMA issuer of query tile 1; also allocates / frees TMEM
+constexpr int kTmemWarp = kMmaWarp1;
 constexpr int kNumThreads = 384;
 // Register split (setmaxnreg): 384 x 168 at launch -> 256 x 208 (softmax) + 128 x 88 (MMA / TMA / TMEM warps)
 constexpr int kSoftmaxRegs = 208;
@@ -69,7 +70,7 @@ struct SmemLayout {
     static constexpr int kBarOff = kKVOff + STAGES * kKVTileBytes;
     // barrier indices
     static constexpr int kBarQFull = 0;                        //        TMA -> MMA     : both query tiles landed
-    static constexpr int kBarQEmpty = 1;                       //        MMA -> TMA     : last Q K^T of the item retired
+    static constexpr int kBarQEmpty = 1;                       //        MMA -> TMA     : last Q K^T of the item retired (both issuers)
     static constexpr int kBarKVFull = 2;
     static constexpr int kBarKVEmpty = kBarKVFull + STAGES;
     static constexpr int kBarSFull = kBarKVEmpty + STAGES;     // [2]    MMA -> softmax : S tile ready in TMEM
@@ -78,8 +79,8 @@ struct SmemLayout {
     static constexpr int kBarOFree = kBarOFull + 2;            // [2]    softmax -> MMA : epilogue has read O out of TMEM
     static constexpr int kBarSchedFull = kBarOFree + 2;        // [2]    TMA -> all     : next work item published
     static constexpr int kBarSchedEmpty = kBarSchedFull + 2;   // [2]    all -> TMA     : work item slot consumed
-    static constexpr int kBarSFree = kBarSchedEmpty + 2;       //        softmax -> MMA : shared S buffer copied into registers
-    static constexpr int kNumBars = kBarSFree + 1;
+    static constexpr int kBarSFree = kBarSchedEmpty + 2;       // [2]    softmax -> MMA : S tile of query tile t copied into registers
+    static constexpr int kNumBars = kBarSFree + 2;
     static constexpr int kSchedItemOff = kBarOff + kNumBars * 8;   // int[2]
     static constexpr int kTmemPtrOff = kSchedItemOff + 8;
     static constexpr int kBytes = kTmemPtrOff + 16;

@@ -18,7 +18,8 @@ nq = (N + 255) // 256
 tiles = sum(min((N + 127) // 128, ((qb * 256 + 255) // 128 + 1)) if causal else (N + 127) // 128 for qb in range(nq)) * B * H   # kv iterations summed over CTAs
 names = ["wait_S", "ld_S", "mask_max_rescale", "exp_pack_st", "st_drain_arrive", "loop_misc"]
 sm = {n: p[i] / (8 * tiles) for i, n in enumerate(names)}      # 8 softmax warps per CTA report, per kv iteration
-mma = {n: p[8 + i] / tiles for i, n in enumerate(["prologue(per CTA, amortised)", "wait_KV", "wait_P0_h0", "issue", "wait_S_free_for_QK0", "wait_S_free_for_QK1", "wait_P0_h1", "wait_P1_h0", "wait_P1_h1"])}
-sm = {k: round(x, 1) for k, x in sm.items()}; mma = {k: round(x, 1) for k, x in mma.items()}
+mnames = ["prologue(per CTA, amortised)", "wait_KV", "wait_P", "issue", "wait_S_buffer", "-"]
+mma = {f"issuer{t}": {n: round(p[8 + 8 * t + i] / tiles, 1) for i, n in enumerate(mnames)} for t in (0, 1)}
+sm = {k: round(x, 1) for k, x in sm.items()}
 print(json.dumps({"lib": os.path.basename(fa_b200.LIB_PATH), "shape": [B, H, N, d, causal], "kv_iterations": tiles, "softmax_warp_cycles_per_kv_iteration": sm,
-                  "softmax_total": sum(sm.values()), "mma_thread_cycles_per_kv_iteration": mma, "mma_total": sum(mma.values())}))
+                  "softmax_total": sum(sm.values()), "mma_thread_cycles_per_kv_iteration": mma, "mma_total": {k: sum(v.values()) for k, v in mma.items()}}))
