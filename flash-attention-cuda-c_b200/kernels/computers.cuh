@@ -33,6 +33,9 @@ namespace fa {
 #define FA_SHARED_S 1
 #endif
 constexpr bool kSharedS = FA_SHARED_S != 0;
+#ifndef FA_PIN_ADDRESSES
+#define FA_PIN_ADDRESSES 1
+#endif
 #ifndef FA_PFREE_WAIT
 #define FA_PFREE_WAIT 0
 #endif
@@ -225,7 +228,10 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
 template <int D, int STAGES, int DT>
 __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, int t) {
     using L = SmemLayout<D, STAGES>;
-    const uint32_t bar0 = smem_base + L::kBarOff;
+    uint32_t bar0 = smem_base + L::kBarOff;
+#if FA_PIN_ADDRESSES
+    asm volatile("" : "+r"(bar0));
+#endif
     const uint32_t s_full = bar0 + 8u * (L::kBarSFull + t);
     const uint32_t p_full0 = bar0 + 8u * (L::kBarPFull + 2 * t);
     const uint32_t p_full1 = p_full0 + 8u;
@@ -236,10 +242,15 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
     const int warp_in_wg = (threadIdx.x / 32) & 3;
     const int lane = threadIdx.x & 31;
     const uint32_t lane_base = uint32_t(warp_in_wg * 32) << 16;
-    const uint32_t tS = tmem_base + lane_base + tmem_s_col(t);
-    const uint32_t tP = tmem_base + lane_base + tmem_p_col(t);
-    const uint32_t tO = tmem_base + lane_base + kTmemO0 + 128u * t;
+    uint32_t tS = tmem_base + lane_base + tmem_s_col(t);
+    uint32_t tP = tmem_base + lane_base + tmem_p_col(t);
+    uint32_t tO = tmem_base + lane_base + kTmemO0 + 128u * t;
     const float c = p.scale_log2;
+#if FA_PIN_ADDRESSES
+    // Keep the loop's addresses in registers: left alone, the compiler re-derives them from %tid / the shared-window
+    // base (S2R, ~25 clk each) at the top of every pass, right on the path between two score tiles.
+    asm volatile("" : "+r"(tS), "+r"(tP), "+r"(tO));
+#endif
 
     FA_PROF_DECL(6);
     int st = 0;      // key tiles this warpgroup has processed so far (barrier phase bookkeeping)

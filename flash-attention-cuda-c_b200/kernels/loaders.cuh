@@ -34,9 +34,14 @@ constexpr int kLoadWarp = 9;
 constexpr int kMmaWarp1 = 10;      // MMA issuer of query tile 1; also allocates / frees TMEM
 constexpr int kTmemWarp = kMmaWarp1;
 constexpr int kNumThreads = 384;
-// Register split (setmaxnreg): 384 x 168 at launch -> 256 x 208 (softmax) + 128 x 88 (MMA / TMA / TMEM warps)
-constexpr int kSoftmaxRegs = 208;
-constexpr int kOtherRegs = 88;
+// Register split (setmaxnreg): 384 x 168 at launch -> 256 x 216 (softmax, no spills) + 128 x 72 (MMA issuers / TMA producer)
+#ifndef FA_SOFTMAX_REGS
+#define FA_SOFTMAX_REGS 216
+#define FA_OTHER_REGS 72
+#endif
+constexpr int kSoftmaxRegs = FA_SOFTMAX_REGS;
+constexpr int kOtherRegs = FA_OTHER_REGS;
+static_assert(256 * kSoftmaxRegs + 128 * kOtherRegs <= 384 * 168, "register split exceeds what the CTA owns at launch (384 threads x 168 registers)");
 // Of every 8 consecutive score pairs, this many take the FMA-pipe exp2 (ex2_emu2) instead of MUFU.EX2.
 #ifndef FA_EMU_PAIRS_PER_8
 #define FA_EMU_PAIRS_PER_8 0

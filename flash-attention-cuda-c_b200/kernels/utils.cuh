@@ -72,8 +72,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+#ifndef FA_TRYWAIT_HINT_NS
+#define FA_TRYWAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if FA_TRYWAIT_HINT_NS > 0
+    // with a suspend-time hint: the thread may sleep in hardware up to that long before try_wait returns false
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(FA_TRYWAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -81,6 +94,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     return ok;
 }
 // Parity wait.  The slow path carries a cycle-count guard so a protocol bug traps (a CUDA error the

@@ -6,8 +6,10 @@ from collections import Counter
 rep = sys.argv[1]
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, data = rows[hi], rows[hi + 1:]
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]       # one block per captured launch: take the last
+hi = his[-1]
+hdr = rows[hi]
+data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
 iS, iSrc, iEx = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
 names = {}
 def bar_name(off, stages=5):
@@ -27,7 +29,7 @@ for k, r in enumerate(data):
     if m:
         off = int(m.group(2), 16) if m.group(2) else -1
         ex = int(r[iEx]) if r[iEx].isdigit() else 0
-        cur = (bar_name(off) if off >= 0x1000 else "kv/ring(dynamic)") ; cur_left = 14
+        cur = bar_name(off) if off >= 0 else "?"; cur_left = 14     # ring barriers: base offset + slot register -> named by the array
     if cur and cur_left > 0 and re.search(r"SYNCS\.PHASECHK|BRA|CS2R|IADD3|IMAD\.X|ISETP|BPT|YIELD|NOP|VIADD|WARPSYNC", src):
         waits[cur] += n
     elif "EXIT" in src:
