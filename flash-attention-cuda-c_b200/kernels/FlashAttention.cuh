@@ -40,9 +40,10 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
     using L = SmemLayout<D, STAGES>;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if ((smem_base & 1023u) != 0) __trap();        // SWIZZLE_128B tiles need 1024-B alignment; see SmemLayout::kDynamicBytes
+    uint8_t* smem_gen = smem_raw;
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kTmemPtrOff);
 
     const int warp = threadIdx.x / 32;
@@ -61,10 +62,10 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t), 128);
             mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t + 1), 128);
             mbar_init(bar0 + 8 * (L::kBarOFull + t), 1);
-            mbar_init(bar0 + 8 * (L::kBarOFree + t), 128);
+            mbar_init(bar0 + 8 * (L::kBarOFree + t), kSoftmaxThreadsPerTile);
             mbar_init(bar0 + 8 * (L::kBarSchedFull + t), 1);
             mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 2 + kSoftmaxWarps);   // both MMA issuers + every softmax warp
-            mbar_init(bar0 + 8 * (L::kBarSFree + t), 128);
+            mbar_init(bar0 + 8 * (L::kBarSFree + t), kSoftmaxThreadsPerTile);
         }
         fence_mbar_init();
     } else if (warp == kLoadWarp && lane == 0) {

@@ -150,7 +150,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
         auto virtual_qk = [&](int j) {
             if constexpr (kSharedS) {
                 wait_s_buffer(j);
-                if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), 128);
+                if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), kSoftmaxThreadsPerTile);
                 __syncwarp();
             }
         };

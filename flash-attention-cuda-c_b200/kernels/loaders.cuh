@@ -28,20 +28,24 @@ constexpr int kHalfCols = 64;      // columns per swizzle-128B half (64 x 2 B = 
 constexpr int kHalfBytes = kBlockN * 128;   // 16 KiB: one half of a 128-row tile
 
 // Warp roles (384 threads = 3 warpgroups)
-constexpr int kSoftmaxWarps = 8;   // warps 0-3: query tile 0, warps 4-7: query tile 1
-constexpr int kMmaWarp0 = 8;       // MMA issuer of query tile 0
-constexpr int kLoadWarp = 9;
-constexpr int kMmaWarp1 = 10;      // MMA issuer of query tile 1; also allocates / frees TMEM
+constexpr int kSoftmaxWarps = 8;   // warps 0-3: query tile 0, warps 4-7: query tile 1; one full score row (128 columns) per thread
+constexpr int kSoftmaxThreadsPerTile = kSoftmaxWarps * 32 / kTilesPerCta;   // arrivals per query tile on s_free / o_free
+constexpr int kMmaWarp0 = kSoftmaxWarps;           // MMA issuer of query tile 0
+constexpr int kLoadWarp = kSoftmaxWarps + 1;       // TMA producer + scheduler (one thread)
+constexpr int kMmaWarp1 = kSoftmaxWarps + 2;       // MMA issuer of query tile 1; also allocates / frees TMEM
 constexpr int kTmemWarp = kMmaWarp1;
-constexpr int kNumThreads = 384;
-// Register split (setmaxnreg): 384 x 168 at launch -> 256 x 216 (softmax, no spills) + 128 x 72 (MMA issuers / TMA producer)
+constexpr int kNumThreads = (kSoftmaxWarps + 4) * 32;
+// Register split (setmaxnreg): 168 per thread at launch -> 256 x 216 (softmax, no spills) + 128 x 72 (MMA issuers / TMA
+// producer); the CTA may not hold more than the 384 x 168 it was launched with.
 #ifndef FA_SOFTMAX_REGS
 #define FA_SOFTMAX_REGS 216
 #define FA_OTHER_REGS 72
 #endif
 constexpr int kSoftmaxRegs = FA_SOFTMAX_REGS;
 constexpr int kOtherRegs = FA_OTHER_REGS;
-static_assert(256 * kSoftmaxRegs + 128 * kOtherRegs <= 384 * 168, "register split exceeds what the CTA owns at launch (384 threads x 168 registers)");
+constexpr int kLaunchRegs = (65536 / kNumThreads) / 8 * 8;     // what __launch_bounds__(kNumThreads, 1) gives every thread
+static_assert(kSoftmaxWarps * 32 * kSoftmaxRegs + 128 * kOtherRegs <= kNumThreads * kLaunchRegs,
+              "register split exceeds what the CTA owns at launch");
 // Of every 8 consecutive score pairs, this many take the FMA-pipe exp2 (ex2_emu2) instead of MUFU.EX2.
 #ifndef FA_EMU_PAIRS_PER_8
 #define FA_EMU_PAIRS_PER_8 0
@@ -89,7 +93,9 @@ struct SmemLayout {
     static constexpr int kSchedItemOff = kBarOff + kNumBars * 8;   // int[2]
     static constexpr int kTmemPtrOff = kSchedItemOff + 8;
     static constexpr int kBytes = kTmemPtrOff + 16;
-    static constexpr int kDynamicBytes = kBytes + 1024;        // slack for manual 1024-B alignment
+    // The dynamic shared-memory window of a kernel without static shared memory starts 1024-B aligned (the kernel traps if
+    // it ever does not), so no alignment slack is reserved.
+    static constexpr int kDynamicBytes = kBytes;
 };
 
 // One work item: a 256-row query block of one (batch, head).
