@@ -5,47 +5,34 @@
 // read-modify-write) and of the per-tile helpers it calls (reference: utils.cuh:17-113).
 //
 // Here the two contractions are tcgen05 MMAs accumulating in tensor memory:
-//   S_t = Q_t K_j^T   (A = Q tile, B = K tile, both K-major in 128B-swizzled smem)   -> TMEM cols [128t, 128t+128)
-//   O_t += P_t V_j    (A = P_t in TMEM as packed 16-bit, B = V tile MN-major in smem) -> TMEM cols [256+128t, ..+D)
-// issued by ONE thread (mmaIssuerThread).  Two softmax warpgroups (one per query tile t) read S
-// with tcgen05.ld in the 32x32b shape — thread i of warp w owns TMEM lane 32*(w%4)+i, i.e. one whole
-// score row, so row max / row sum need no shuffles — and keep the online-softmax state
-// (running max m, running sum l) in registers:
+//   S   = Q_t K_j^T   (A = Q tile, B = K tile, both K-major in 128B-swizzled smem)    -> the shared S buffer
+//   O_t += P_t V_j    (A = P_t in TMEM as packed 16-bit, B = V tile MN-major in smem) -> O_t
+// issued by TWO issuer warps (one per query tile t; one elected lane per batch of MMAs).  Two softmax
+// warpgroups (one per query tile) read S with tcgen05.ld in the 32x32b shape — thread i of warp w owns TMEM
+// lane 32*(w%4)+i, i.e. one whole score row, so row max / row sum need no shuffles — and keep the
+// online-softmax state (running max m, running sum l) in registers:
 //   m' = max(m, rowmax(S));  P = exp2(S*c - m*c)  (c = scale*log2 e);  l += rowsum(P)
 // Normalisation by 1/l is deferred to the epilogue (the reference normalises every tile,
 // utils.cuh:79-80).  O is rescaled lazily: only when a row's max grew by more than 2^8 since the max
 // in use (then O *= exp2((m_used - m')c) through a tcgen05.ld / tcgen05.st round trip).
-// TMEM map (512 columns, kSharedS = true, the default):  S 0..127 | P_0 128..191 | P_1 192..255 | O_0 256..383 | O_1 384..511.
+//
+// TMEM map (512 columns):  S 0..127 | P_0 128..191 | P_1 192..255 | O_0 256..383 | O_1 384..511.
 // ONE score buffer is shared by both query tiles: a tile's softmax warpgroup copies its S row into registers
 // within ~100 clk of the MMA retiring and hands the buffer back (s_free), so the buffer is free long before the
-// tensor pipe needs it again; P_t (two 16-bit values per 32-bit column) has columns of its own.  That removes the
-// S/P aliasing of the first design (P_t over the head of S_t), under which "Q_t K_{j+1}^T" had to queue behind
-// "P_t V_j" and the tensor pipe idled for a third of every step: now the next score tile of a query tile is
-// computed while its softmax warpgroup is still exponentiating the current one, and the warpgroups never wait for S.
-// kSharedS = false keeps the aliased layout (S_t at 128t, P_t over its first 64 columns) for comparison builds.
+// tensor pipe needs it again; P_t (two 16-bit values per 32-bit column) has columns of its own.  With two S tiles
+// and P_t aliased over the head of S_t (the first design of this kernel) "Q_t K_{j+1}^T" had to queue behind
+// "P_t V_j" and the tensor pipe idled for a third of every step; here the next score tile of a query tile is
+// computed while its softmax warpgroup is still exponentiating the current one.
 #pragma once
 
 #include "loaders.cuh"
 
 namespace fa {
 
-#ifndef FA_SHARED_S
-#define FA_SHARED_S 1
-#endif
-constexpr bool kSharedS = FA_SHARED_S != 0;
-#ifndef FA_PIN_ADDRESSES
-#define FA_PIN_ADDRESSES 1
-#endif
-#ifndef FA_PFREE_WAIT
-#define FA_PFREE_WAIT 0
-#endif
-constexpr int kPFreeWait = FA_PFREE_WAIT; // where the softmax pass checks that P_t V_{j-1} retired: 0 = before the exponentials, 1 = before the first P store, 2 = after the first quarter
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemS = 0;       // the shared S buffer
 constexpr uint32_t kTmemO0 = 256;    // O tile t at columns 256 + 128*t
-// S tile of query tile t: the one shared buffer at column 0, or (aliased layout) columns 128*t
-__host__ __device__ constexpr uint32_t tmem_s_col(int t) { return kSharedS ? 0u : 128u * uint32_t(t); }
-// P tile of query tile t: columns 128 + 64*t, or (aliased layout) the head of its own S tile
-__host__ __device__ constexpr uint32_t tmem_p_col(int t) { return kSharedS ? 128u + 64u * uint32_t(t) : 128u * uint32_t(t); }
+__host__ __device__ constexpr uint32_t tmem_p_col(int t) { return 128u + 64u * uint32_t(t); }   // P tile of query tile t
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
 
 // ------------------------------------------------------------------------------------------------
@@ -56,8 +43,7 @@ constexpr float kRescaleThreshold = 8.0f;   // log2 units
 // pipe and every mbarrier wait it makes (~100 clk even when the barrier has already completed) is a bubble in the
 // pipe.  With two issuers the bubbles of one are filled by the MMAs of the other, and the order in which the two query
 // tiles' MMAs reach the pipe follows readiness instead of a fixed program order.
-// Per key tile j issuer t does, shared-S layout:   Q_tK_{j+1} (after the previous S tile has been copied out), P_tV_j
-//                                aliased layout:    P_tV_j, Q_tK_{j+1}
+// Per key tile j issuer t does:   Q_tK_{j+1} (once the previous S tile has been copied out of the shared buffer), P_tV_j
 // K/V slots and the Q tiles are handed back to the producer by BOTH issuers (barrier count 2): a tcgen05.commit when the
 // issuer multiplied with the tile, a plain arrive when it did not (causal blocks: the early query tile stops one key
 // tile sooner) — in both cases only after it has seen the slot full, which keeps the phases in step.
@@ -76,7 +62,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
     const uint64_t desc_k_major = umma_desc_sw128(0, 16, 1024);             // Q and K tiles (K-major)
     const uint64_t desc_mn_major = umma_desc_sw128(0, kHalfBytes, 1024);    // V tile (MN-major), 64-column halves 16 KiB apart
     const uint64_t q_desc = desc_k_major + ((smem_base + L::kQOff + t * L::kQTileBytes) >> 4);
-    const uint32_t s_tmem = tmem_base + tmem_s_col(t);
+    const uint32_t s_tmem = tmem_base + kTmemS;
     const uint32_t p_tmem = tmem_base + tmem_p_col(t);
     const uint32_t o_tmem = tmem_base + kTmemO0 + 128u * t;
     FA_PROF_DECL(6);
@@ -148,11 +134,9 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
             }
         };
         auto virtual_qk = [&](int j) {
-            if constexpr (kSharedS) {
-                wait_s_buffer(j);
-                if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), kSoftmaxThreadsPerTile);
-                __syncwarp();
-            }
+            wait_s_buffer(j);
+            if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), kSoftmaxThreadsPerTile);
+            __syncwarp();
         };
         auto pv = [&](int j) {
             const uint32_t ph = (st + j) & 1;
@@ -172,7 +156,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
         };
         auto qk = [&](int j) {
             FA_PROF_MARK(3);
-            if constexpr (kSharedS) wait_s_buffer(j);
+            wait_s_buffer(j);
             FA_PROF_MARK(4);             // waiting for the shared S buffer
             issue_qk(slot_addr(it0 + 2 * j), empty_bar(it0 + 2 * j), j + 1 == nt);
             FA_PROF_MARK(3);
@@ -191,25 +175,18 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
         for (int j = 0; j < n; ++j) {
             const int it_v = it0 + 2 * j + 1, it_k = it0 + 2 * j + 2;
             const bool has_next = j + 1 < n;
-            if constexpr (!kSharedS) {
-                wait_full(it_v);
-                FA_PROF_MARK(1);         // waiting for K/V tiles
-                if (j < nt) pv(j); else arrive(empty_bar(it_v));
-            }
             if (has_next) {
                 wait_full(it_k);
-                FA_PROF_MARK(1);
+                FA_PROF_MARK(1);         // waiting for K/V tiles
                 if (j + 1 < nt) qk(j + 1);
                 else {
                     virtual_qk(j + 1);
                     arrive(empty_bar(it_k));
                 }
             }
-            if constexpr (kSharedS) {
-                wait_full(it_v);
-                FA_PROF_MARK(1);
-                if (j < nt) pv(j); else arrive(empty_bar(it_v));
-            }
+            wait_full(it_v);
+            FA_PROF_MARK(1);
+            if (j < nt) pv(j); else arrive(empty_bar(it_v));
         }
         st += nt;
         sq += n;
@@ -229,9 +206,7 @@ template <int D, int STAGES, int DT>
 __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, int t) {
     using L = SmemLayout<D, STAGES>;
     uint32_t bar0 = smem_base + L::kBarOff;
-#if FA_PIN_ADDRESSES
-    asm volatile("" : "+r"(bar0));
-#endif
+    asm volatile("" : "+r"(bar0));     // keep in a register (see below)
     const uint32_t s_full = bar0 + 8u * (L::kBarSFull + t);
     const uint32_t p_full0 = bar0 + 8u * (L::kBarPFull + 2 * t);
     const uint32_t p_full1 = p_full0 + 8u;
@@ -242,15 +217,13 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
     const int warp_in_wg = (threadIdx.x / 32) & 3;
     const int lane = threadIdx.x & 31;
     const uint32_t lane_base = uint32_t(warp_in_wg * 32) << 16;
-    uint32_t tS = tmem_base + lane_base + tmem_s_col(t);
+    uint32_t tS = tmem_base + lane_base + kTmemS;
     uint32_t tP = tmem_base + lane_base + tmem_p_col(t);
     uint32_t tO = tmem_base + lane_base + kTmemO0 + 128u * t;
     const float c = p.scale_log2;
-#if FA_PIN_ADDRESSES
     // Keep the loop's addresses in registers: left alone, the compiler re-derives them from %tid / the shared-window
     // base (S2R, ~25 clk each) at the top of every pass, right on the path between two score tiles.
     asm volatile("" : "+r"(tS), "+r"(tP), "+r"(tO));
-#endif
 
     FA_PROF_DECL(6);
     int st = 0;      // key tiles this warpgroup has processed so far (barrier phase bookkeeping)
@@ -276,10 +249,8 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
 #pragma unroll
             for (int q = 0; q < kBlockN / 32; ++q) tmem_ld32(tS + 32u * q, r + 32 * q);
             tc_wait_ld();
-            if constexpr (kSharedS) {
-                tc_fence_before();
-                mbar_arrive(s_free);     // the score row is in registers: the shared S buffer may be overwritten
-            }
+            tc_fence_before();
+            mbar_arrive(s_free);         // the score row is in registers: the shared S buffer may be overwritten
             FA_PROF_MARK(1);             // tcgen05.ld of the score row
 
             const int kv0 = j * kBlockN;
@@ -351,23 +322,17 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                     pk[cc / 2 + 1] = pack16<DT>(x1.x, x1.y);
                 }
             };
-            // P_t has columns of its own: P_t V_{j-1} must have retired before they are overwritten (it was issued when
-            // the previous pass ended, so it almost always has)
-            auto wait_p_free = [&]() {
-                if constexpr (kSharedS) {
-                    if (j > 0) {
-                        mbar_wait(o_full, ph ^ 1);
-                        tc_fence_after();
-                    }
-                }
-            };
-            if constexpr (kPFreeWait == 0) wait_p_free();
+            // P_t V_{j-1} must have retired before the P columns are overwritten.  Checked here, before the exponentials,
+            // rather than right before the first store: measured 3-6 % faster (a warpgroup that has to wait leaves the
+            // MUFU unit to the other one, and the stores stay where the scheduler wants them).
+            if (j > 0) {
+                mbar_wait(o_full, ph ^ 1);
+                tc_fence_after();
+            }
             {
                 uint32_t pk[32];
                 exp_quarter(0, pk);
-                if constexpr (kPFreeWait == 2) wait_p_free();
                 exp_quarter(1, pk + 16);
-                if constexpr (kPFreeWait == 1) wait_p_free();
                 tmem_st32(tP, pk);                 // keys 0..63 of P
             }
             {
