@@ -251,6 +251,16 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             tc_wait_ld();
             tc_fence_before();
             mbar_arrive(s_free);         // the score row is in registers: the shared S buffer may be overwritten
+#ifdef FA_PHASE_PROFILE
+            // lag between the two warpgroups: clocks since the OTHER warpgroup last took an S tile (warp 0 of each reports)
+            if ((threadIdx.x & 127) == 0) {
+                uint32_t now, other;
+                asm volatile("mov.u32 %0, %%clock;" : "=r"(now));
+                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(other) : "r"(smem_base + L::kTmemPtrOff + 8u + 4u * (1 - t)) : "memory");
+                asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_base + L::kTmemPtrOff + 8u + 4u * t), "r"(now) : "memory");
+                if (p.prof && j > 0) atomicAdd(p.prof + 24 + t, (unsigned long long)(now - other));
+            }
+#endif
             FA_PROF_MARK(1);             // tcgen05.ld of the score row
 
             const int kv0 = j * kBlockN;

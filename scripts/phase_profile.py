@@ -21,5 +21,6 @@ sm = {n: p[i] / (8 * tiles) for i, n in enumerate(names)}      # 8 softmax warps
 mnames = ["prologue(per CTA, amortised)", "wait_KV", "wait_P", "issue", "wait_S_buffer", "-"]
 mma = {f"issuer{t}": {n: round(p[8 + 8 * t + i] / tiles, 1) for i, n in enumerate(mnames)} for t in (0, 1)}
 sm = {k: round(x, 1) for k, x in sm.items()}
+lag = {f"tile{t}_pickup_after_other_pickup": round(p[24 + t] / max(tiles - B * H * nq, 1), 1) for t in (0, 1)}   # per kv iteration with j > 0
 print(json.dumps({"lib": os.path.basename(fa_b200.LIB_PATH), "shape": [B, H, N, d, causal], "kv_iterations": tiles, "softmax_warp_cycles_per_kv_iteration": sm,
-                  "softmax_total": sum(sm.values()), "mma_thread_cycles_per_kv_iteration": mma, "mma_total": {k: sum(v.values()) for k, v in mma.items()}}))
+                  "softmax_total": sum(sm.values()), "warpgroup_lag_cycles": lag, "mma_thread_cycles_per_kv_iteration": mma, "mma_total": {k: sum(v.values()) for k, v in mma.items()}}))
