@@ -141,6 +141,56 @@ def test_16bit_all_ones_known_answer():
         assert torch.allclose(o, torch.ones_like(o), atol=1e-2)
 
 
+@pytest.mark.parametrize("dtype,d", [(torch.bfloat16, 128), (torch.float16, 64), (torch.float32, 64)])
+@pytest.mark.parametrize("nq,nk", [(333, 333), (1, 129), (257, 100)])
+def test_no_write_outside_the_output_rows(dtype, d, nq, nk):
+    # compute-sanitizer is not available on this pool, so the bounds check is our own: O is a view of rows
+    # [3, 3+Nq) inside a sentinel-filled buffer (ragged Nq: the last 128-row tile hangs over the end), LSE sits between
+    # two sentinel bands; nothing outside the view may change and everything inside must be overwritten.
+    B, H = 2, 3
+    q, k, v = (t.cuda() for t in _inputs(B, H, H, nq, nk, d, dtype, seed=nq + d))
+    sent = 512.0
+    big = torch.full((B, H, nq + 8, d), sent, dtype=dtype, device="cuda")
+    out = big[:, :, 3:3 + nq, :]
+    lse_big = torch.full((B * H * nq + 64,), sent, dtype=torch.float32, device="cuda")
+    strides = (fa_b200.ctypes.c_longlong * 12)(*(list(q.stride()[:3]) + list(k.stride()[:3]) + list(v.stride()[:3]) + list(out.stride()[:3])))
+    for causal in (0, 1):
+        big.fill_(sent)
+        lse_big.fill_(sent)
+        rc = fa_b200.lib().fa_fwd_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_big.data_ptr() + 32 * 4,
+                                          B, H, H, nq, nk, d, fa_b200._dtype_code(q), 0.0, causal, strides, fa_b200._stream_ptr(q))
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert (big[:, :, :3] == sent).all() and (big[:, :, 3 + nq:] == sent).all(), "write outside the output rows"
+        assert (lse_big[:32] == sent).all() and (lse_big[32 + B * H * nq:] == sent).all(), "write outside the LSE range"
+        o_ref, lse_ref = oracle.attention_fwd(q.float().cpu().numpy(), k.float().cpu().numpy(), v.float().cpu().numpy(),
+                                              causal=bool(causal), return_lse=True)
+        tol = TOL16 if dtype != torch.float32 else RTOL32 * max(np.abs(o_ref).max(), 1.0)
+        assert np.abs(out.float().cpu().numpy() - o_ref).max() <= tol
+        got = lse_big[32:32 + B * H * nq].view(B, H, nq).cpu().numpy()
+        fin = np.isfinite(lse_ref)
+        assert (np.isfinite(got) == fin).all()      # every LSE slot was written (no sentinel left)
+        np.testing.assert_allclose(got[fin], lse_ref[fin], rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_nan_in_one_query_row_stays_in_that_row(causal):
+    # NaN / Inf guard: a poisoned query row yields a non-finite output row (as in check.py's softmax) and must neither hang
+    # the barrier protocol nor leak into any other row of the tile
+    q, k, v = _inputs(1, 2, 2, 300, 300, 128, torch.bfloat16, seed=5)
+    q[0, 1, 130, 7] = float("nan")
+    q[0, 0, 5, :] = float("inf")
+    o = fa_b200.attention_forward(q.cuda(), k.cuda(), v.cuda(), causal=causal).float().cpu().numpy()
+    bad = np.zeros((1, 2, 300), dtype=bool)
+    bad[0, 1, 130] = bad[0, 0, 5] = True
+    assert not np.isfinite(o[bad]).any()
+    qc = q.clone()
+    qc[0, 1, 130, 7] = 0.0
+    qc[0, 0, 5, :] = 0.0
+    o_ref = oracle.attention_fwd(qc.float().numpy(), k.float().numpy(), v.float().numpy(), causal=causal)
+    assert np.abs(o[~bad] - o_ref[~bad]).max() <= TOL16
+
+
 def test_config2_gpt2_shape_fp16():
     # BASELINE.json configs[1]: B=4 H=12 N=1024 d=64 non-causal fp16
     _check(*_inputs(4, 12, 12, 1024, 1024, 64, torch.float16), causal=False)
