@@ -80,6 +80,10 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // Cycle counter for A/B work (fa_debug_set_profile_buffer): the otherwise idle last warp times the CTA from here to the
+    // final barrier; prof[30] = max over CTAs, prof[31] = sum.  Wall-clock A/B on a power-capped GPU is too noisy.
+    long long cta_t0 = 0;
+    if (p.prof != nullptr && threadIdx.x == kNumThreads - 32) cta_t0 = clock64();
 
     if (warp < kSoftmaxWarps) {
         reg_inc<kSoftmaxRegs>();
@@ -100,6 +104,11 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == kTmemWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
+    }
+    if (p.prof != nullptr && threadIdx.x == kNumThreads - 32) {
+        const unsigned long long dt = (unsigned long long)(clock64() - cta_t0);
+        atomicMax(p.prof + 30, dt);
+        atomicAdd(p.prof + 31, dt);
     }
 }
 
