@@ -229,6 +229,7 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     fa::FwdParams p;
     p.O = O; p.lse = lse; p.acc_o = acc_o; p.acc_lse = acc_lse; p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
     p.o_stride_b = s[9]; p.o_stride_h = s[10]; p.o_stride_n = s[11];
+    p.o_vec32 = (reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0) ? 1 : 0;
     p.scale = sc; p.scale_log2 = sc * 1.4426950408889634f;
     p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
     p.prof = g_prof;

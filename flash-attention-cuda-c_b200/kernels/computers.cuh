@@ -385,10 +385,18 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         h[i] = pack16<DT>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+                    // Every lane writes its own row (rows are o_stride_n apart), so a store instruction touches 32 different
+                    // lines whatever its width: 256-bit stores (one full 32-byte sector per lane) halve the number of such
+                    // instructions; measured -0.9 % cycles at N = 8K, -3 % at N <= 2K against 128-bit stores.
                     if (row_ok) {
+                        if (p.o_vec32) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            st_global_v4(orow + 32 * q + 8 * i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                            for (int i = 0; i < 2; ++i) st_global_v8(orow + 32 * q + 16 * i, h + 8 * i);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                st_global_v4(orow + 32 * q + 8 * i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                        }
                     }
                 }
                 tc_fence_before();

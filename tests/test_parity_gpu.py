@@ -173,6 +173,22 @@ def test_no_write_outside_the_output_rows(dtype, d, nq, nk):
         np.testing.assert_allclose(got[fin], lse_ref[fin], rtol=0, atol=2e-3)
 
 
+@pytest.mark.parametrize("col_off", [0, 8])
+def test_output_view_alignment_paths(col_off):
+    # the epilogue uses 256-bit stores when O is 32-byte aligned and 128-bit stores otherwise: an output view that starts
+    # 16 bytes into a wider, sentinel-filled buffer takes the second path; the columns beside the view must stay untouched
+    B, H, n, d = 1, 3, 300, 128
+    q, k, v = (t.cuda() for t in _inputs(B, H, H, n, n, d, torch.bfloat16, seed=77))
+    big = torch.full((B, H, n, d + 16), 512.0, dtype=torch.bfloat16, device="cuda")
+    out = big[..., col_off:col_off + d]
+    assert out.data_ptr() % 32 == (16 if col_off else 0)
+    fa_b200.attention_forward(q, k, v, causal=True, out=out)
+    torch.cuda.synchronize()
+    assert (big[..., :col_off] == 512.0).all() and (big[..., col_off + d:] == 512.0).all()
+    o_ref = oracle.attention_fwd(q.float().cpu().numpy(), k.float().cpu().numpy(), v.float().cpu().numpy(), causal=True)
+    assert np.abs(out.float().cpu().numpy() - o_ref).max() <= TOL16
+
+
 @pytest.mark.parametrize("causal", [False, True])
 def test_nan_in_one_query_row_stays_in_that_row(causal):
     # NaN / Inf guard: a poisoned query row yields a non-finite output row (as in check.py's softmax) and must neither hang
