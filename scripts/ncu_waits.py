@@ -15,7 +15,7 @@ names = {}
 def bar_name(off, stages=5):
     i = (off & 0xfff) // 8
     tbl = [("q_full", 1), ("q_empty", 1), ("kv_full", stages), ("kv_empty", stages), ("s_full", 2), ("p_full", 4), ("o_full", 2), ("o_free", 2),
-           ("sched_full", 2), ("sched_empty", 2), ("s_free", 1)]
+           ("sched_full", 2), ("sched_empty", 2), ("s_free", 2)]
     for n, c in tbl:
         if i < c: return n
         i -= c
@@ -25,15 +25,18 @@ waits = Counter(); other = 0; cur = None; cur_left = 0
 for k, r in enumerate(data):
     n = int(r[iS]) if r[iS].isdigit() else 0
     src = r[iSrc]
-    m = re.search(r"SYNCS\.PHASECHK\.TRANS64\.TRYWAIT\s+\w+, \[(\w+)\+URZ(?:\+(0x[0-9a-f]+))?\]", src)
+    m = re.search(r"SYNCS\.PHASECHK\.TRANS64\.TRYWAIT\s+\w+, \[(?:(R\w+)\+)?(UR\w+)(?:\+(0x[0-9a-f]+))?\]", src)
     if m:
-        off = int(m.group(2), 16) if m.group(2) else -1
-        ex = int(r[iEx]) if r[iEx].isdigit() else 0
-        cur = bar_name(off) if off >= 0 else "?"; cur_left = 14     # ring barriers: base offset + slot register -> named by the array
+        off = int(m.group(3), 16) if m.group(3) else -1
+        if m.group(1) and m.group(2) != "URZ" and off >= 0 and (off & 0xfff) == 0:
+            cur = "ring barrier (register-indexed: kv_full / kv_empty / sched)"     # base of the barrier block + an index register
+        else:
+            cur = bar_name(off) if off >= 0 else "?"
+        cur_left = 14
     if cur and cur_left > 0 and re.search(r"SYNCS\.PHASECHK|BRA|CS2R|IADD3|IMAD\.X|ISETP|BPT|YIELD|NOP|VIADD|WARPSYNC", src):
         waits[cur] += n
-    elif "EXIT" in src:
-        waits["exit barrier (idle warps)"] += n
+    elif "EXIT" in src or "BAR.SYNC" in src:
+        waits["CTA barriers / exit (idle warp)"] += n
     else:
         other += n
     cur_left -= 1
