@@ -112,11 +112,11 @@ int* next_counter(cudaStream_t st, int* sm_count_out) {
 }
 
 // ---- tcgen05 path ----------------------------------------------------------------------------------
-template <int D, int STAGES, int DT>
+template <int D, int STAGES, int DT, bool OVEC32>
 int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, fa::FwdParams p,
                  cudaStream_t st) {
     using L = fa::SmemLayout<D, STAGES>;
-    auto kern = fa::fwdSm100Kernel<D, STAGES, DT>;
+    auto kern = fa::fwdSm100Kernel<D, STAGES, DT, OVEC32>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] {
@@ -229,17 +229,19 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     fa::FwdParams p;
     p.O = O; p.lse = lse; p.acc_o = acc_o; p.acc_lse = acc_lse; p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
     p.o_stride_b = s[9]; p.o_stride_h = s[10]; p.o_stride_n = s[11];
-    p.o_vec32 = (reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0) ? 1 : 0;
     p.scale = sc; p.scale_log2 = sc * 1.4426950408889634f;
     p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
     p.prof = g_prof;
 
+    // 256-bit epilogue stores need every output row to start 32-byte aligned (carry mode does not write O at all)
+    const bool v32 = !carry && reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0;
+    const bool bf = dtype == FA_DTYPE_BF16;
     if (d == 128) {
-        return dtype == FA_DTYPE_BF16 ? launch_sm100<128, 5, fa::kBF16>(tq, tk, tv, p, st)
-                                      : launch_sm100<128, 5, fa::kF16>(tq, tk, tv, p, st);
+        if (v32) return bf ? launch_sm100<128, 5, fa::kBF16, true>(tq, tk, tv, p, st) : launch_sm100<128, 5, fa::kF16, true>(tq, tk, tv, p, st);
+        return bf ? launch_sm100<128, 5, fa::kBF16, false>(tq, tk, tv, p, st) : launch_sm100<128, 5, fa::kF16, false>(tq, tk, tv, p, st);
     }
-    return dtype == FA_DTYPE_BF16 ? launch_sm100<64, 8, fa::kBF16>(tq, tk, tv, p, st)
-                                  : launch_sm100<64, 8, fa::kF16>(tq, tk, tv, p, st);
+    if (v32) return bf ? launch_sm100<64, 8, fa::kBF16, true>(tq, tk, tv, p, st) : launch_sm100<64, 8, fa::kF16, true>(tq, tk, tv, p, st);
+    return bf ? launch_sm100<64, 8, fa::kBF16, false>(tq, tk, tv, p, st) : launch_sm100<64, 8, fa::kF16, false>(tq, tk, tv, p, st);
 }
 
 // ---- host-buffer pipeline state ---------------------------------------------------------------------

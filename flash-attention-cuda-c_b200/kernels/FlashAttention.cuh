@@ -6,7 +6,8 @@
 //                                                    int batchSize, int numHeads, int seqLen, float scale, bool is_causal)
 // (reference: kernels/FlashAttention.cuh:59-63), and adds the B200-native kernel the C-ABI launcher in
 // FlashAttention.cu dispatches to:
-//   fa::fwdSm100Kernel<D, STAGES, DT>   — warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16)
+//   fa::fwdSm100Kernel<D, STAGES, DT, OVEC32> — warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16; OVEC32: O is
+//                                        32-byte aligned, so the epilogue may use 256-bit stores)
 //   fa::fwdFp32Kernel<D>                — exact-fp32 CUDA-core kernel for fp32 I/O
 // The compat template is launched by the *caller* with a grid/block/shared-memory size of its own choosing
 // (reference: tests/main.cu:51-61 uses grid 1, (QT+2)*32 threads, (3QT+4R)*D*4 bytes), so it cannot take TMA
@@ -35,7 +36,7 @@ namespace fa {
 //   warp  9    TMA producer + scheduler (one thread)
 //   warp 10    TMEM allocator, then MMA issuer for query tile 1
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT>
+template <int D, int STAGES, int DT, bool OVEC32>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -87,7 +88,7 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     if (warp < kSoftmaxWarps) {
         reg_inc<kSoftmaxRegs>();
-        softmaxWarpgroup<D, STAGES, DT>(smem_base, tmem_base, p, warp / 4);
+        softmaxWarpgroup<D, STAGES, DT, OVEC32>(smem_base, tmem_base, p, warp / 4);
     } else {
         reg_dec<kOtherRegs>();
         if (warp == kMmaWarp0) {

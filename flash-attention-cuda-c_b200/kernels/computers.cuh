@@ -202,7 +202,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
 // epilogue (O/l -> global, optional LSE).  Persistent: loops over the published work items; the epilogue of one item
 // overlaps the next item's first Q K^T.
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT>
+template <int D, int STAGES, int DT, bool OVEC32>
 __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, int t) {
     using L = SmemLayout<D, STAGES>;
     uint32_t bar0 = smem_base + L::kBarOff;
@@ -387,9 +387,10 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                         h[i] = pack16<DT>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
                     // Every lane writes its own row (rows are o_stride_n apart), so a store instruction touches 32 different
                     // lines whatever its width: 256-bit stores (one full 32-byte sector per lane) halve the number of such
-                    // instructions; measured -0.9 % cycles at N = 8K, -3 % at N <= 2K against 128-bit stores.
+                    // instructions; measured -0.9 % cycles at N = 8K, -3 % at N <= 2K against 128-bit stores.  The choice is a
+                    // template parameter: as a run-time branch on a kernel parameter it gave most of that back at N <= 2K.
                     if (row_ok) {
-                        if (p.o_vec32) {
+                        if constexpr (OVEC32) {
 #pragma unroll
                             for (int i = 0; i < 2; ++i) st_global_v8(orow + 32 * q + 16 * i, h + 8 * i);
                         } else {

@@ -59,7 +59,6 @@ struct FwdParams {
     float* acc_lse;          // carry mode: fp32 [B, Hq, Nq] running log-sum-exp, updated in place
     int B, Hq, Hkv, Nq, Nk;
     long long o_stride_b, o_stride_h, o_stride_n;   // in elements; innermost (d) stride is 1
-    int o_vec32;             // O base and row/head/batch strides are 32-byte aligned: the epilogue may use 256-bit stores
     float scale;             // softmax scale (1/sqrt(d) by default)
     float scale_log2;        // scale * log2(e)
     int causal;              // 0/1
