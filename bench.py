@@ -24,6 +24,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: whatever NCCL has to say (NCCL_DEBUG=VERSION / INFO) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "flash-attention-cuda-c_b200")
 for p in (ROOT, PKG):
