@@ -67,6 +67,7 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(bar0 + 8 * (L::kBarSchedFull + t), 1);
             mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 2 + kSoftmaxWarps);   // both MMA issuers + every softmax warp
             mbar_init(bar0 + 8 * (L::kBarSFree + t), kSoftmaxThreadsPerTile);
+            mbar_init(bar0 + 8 * (L::kBarOHalf + t), 1);
         }
         fence_mbar_init();
     } else if (warp == kLoadWarp && lane == 0) {

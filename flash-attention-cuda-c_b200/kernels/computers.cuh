@@ -97,6 +97,8 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
             if (half == 1) {
                 tc_commit(bar(L::kBarOFull + t));
                 tc_commit(release_bar);
+            } else if (kSplitOFull<D>) {
+                tc_commit(bar(L::kBarOHalf + t));
             }
         }
         __syncwarp();
@@ -213,6 +215,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
     const uint32_t o_full = bar0 + 8u * (L::kBarOFull + t);
     const uint32_t o_free = bar0 + 8u * (L::kBarOFree + t);
     const uint32_t s_free = bar0 + 8u * (L::kBarSFree + t);
+    const uint32_t o_half = bar0 + 8u * (L::kBarOHalf + t);
 
     const int warp_in_wg = (threadIdx.x / 32) & 3;
     const int lane = threadIdx.x & 31;
@@ -336,7 +339,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             // rather than right before the first store: measured 3-6 % faster (a warpgroup that has to wait leaves the
             // MUFU unit to the other one, and the stores stay where the scheduler wants them).
             if (j > 0) {
-                mbar_wait(o_full, ph ^ 1);
+                mbar_wait(kSplitOFull<D> ? o_half : o_full, ph ^ 1);
                 tc_fence_after();
             }
             {
@@ -352,6 +355,10 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 tc_fence_before();
                 mbar_arrive(p_full0);              // MMA may start P V on keys 0..63
                 exp_quarter(3, pk + 16);
+                if (kSplitOFull<D> && j > 0) {
+                    mbar_wait(o_full, ph ^ 1);
+                    tc_fence_after();
+                }
                 tmem_st32(tP + 32u, pk);           // keys 64..127 of P
             }
             FA_PROF_MARK(3);             // exp2 / pack / tcgen05.st issue

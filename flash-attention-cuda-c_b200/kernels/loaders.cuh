@@ -52,6 +52,18 @@ static_assert(kSoftmaxWarps * 32 * kSoftmaxRegs + 128 * kOtherRegs <= kNumThread
 #endif
 constexpr int kEmuPairsPer8 = FA_EMU_PAIRS_PER_8;
 
+// Split wait for the previous P V (d = 128 only): the softmax warpgroup waits for the FIRST half of P_t V_{j-1} (o_half, an
+// extra tcgen05.commit) before it overwrites the first half of P_t, and for the second half (o_full) only right before it
+// overwrites the second half.  Measured on the shipped (un-instrumented) build: 2,712 -> 2,671 clk per step causal 8K,
+// 2,670 -> 2,614 non-causal; wall clock +1 .. +4 % in bench.py, +0.9 .. +1.4 % held for 0.5 s under the power cap.  (The
+// FA_PHASE_PROFILE build shows the opposite, 2,813 -> 2,940: its clock reads perturb exactly this hand-off; trust
+// scripts/cycles.py.)  At d = 64, where P V is half as long, it loses 3.6 % and stays off.
+#ifndef FA_SPLIT_OFULL
+#define FA_SPLIT_OFULL 1
+#endif
+template <int D>
+constexpr bool kSplitOFull = (FA_SPLIT_OFULL != 0) && D == 128;
+
 struct FwdParams {
     void* O;                 // output, same dtype as Q
     float* lse;              // optional [B, Hq, Nq] log-sum-exp (natural log), may be null
@@ -89,7 +101,8 @@ struct SmemLayout {
     static constexpr int kBarSchedFull = kBarOFree + 2;        // [2]    TMA -> all     : next work item published
     static constexpr int kBarSchedEmpty = kBarSchedFull + 2;   // [2]    all -> TMA     : work item slot consumed
     static constexpr int kBarSFree = kBarSchedEmpty + 2;       // [2]    softmax -> MMA : S tile of query tile t copied into registers
-    static constexpr int kNumBars = kBarSFree + 2;
+    static constexpr int kBarOHalf = kBarSFree + 2;            // [2]    MMA -> softmax : first half (keys 0..63) of P*V of this step retired
+    static constexpr int kNumBars = kBarOHalf + 2;
     static constexpr int kSchedItemOff = kBarOff + kNumBars * 8;   // int[2]
     static constexpr int kTmemPtrOff = kSchedItemOff + 8;
     static constexpr int kBytes = kTmemPtrOff + 16;

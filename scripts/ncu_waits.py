@@ -15,7 +15,7 @@ names = {}
 def bar_name(off, stages=5):
     i = (off & 0xfff) // 8
     tbl = [("q_full", 1), ("q_empty", 1), ("kv_full", stages), ("kv_empty", stages), ("s_full", 2), ("p_full", 4), ("o_full", 2), ("o_free", 2),
-           ("sched_full", 2), ("sched_empty", 2), ("s_free", 2)]
+           ("sched_full", 2), ("sched_empty", 2), ("s_free", 2), ("o_half", 2)]
     for n, c in tbl:
         if i < c: return n
         i -= c
