@@ -53,7 +53,7 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == kMmaWarp0 && lane == 0) {
         const uint32_t bar0 = smem_base + L::kBarOff;
         mbar_init(bar0 + 8 * L::kBarQFull, 1);
-        mbar_init(bar0 + 8 * L::kBarQEmpty, 2);                     // both MMA issuers
+        mbar_init(bar0 + 8 * L::kBarQEmpty, kIssuerByType<D> ? 1 : 2); // both MMA issuers (split by type: the Q K^T issuer alone)
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar0 + 8 * (L::kBarKVFull + s), 1);
             mbar_init(bar0 + 8 * (L::kBarKVEmpty + s), 2);          // both MMA issuers
@@ -93,9 +93,11 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     } else {
         reg_dec<kOtherRegs>();
         if (warp == kMmaWarp0) {
-            mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 0);
+            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 0);
+            else mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 0);
         } else if (warp == kMmaWarp1) {
-            mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 1);
+            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 1);
+            else mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 1);
         } else if (warp == kLoadWarp) {
             if (lane == 0) tmaLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, p);
         }

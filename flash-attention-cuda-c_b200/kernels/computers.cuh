@@ -200,6 +200,128 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
 }
 
 // ------------------------------------------------------------------------------------------------
+// MMA issuers split by TYPE instead of by query tile (FA_ISSUER_BY_TYPE): warp kMmaWarp0 issues every Q K^T (both query
+// tiles), warp kMmaWarp1 every P V.  tcgen05.mma issue blocks while the pipe's queue is full, so with one issuer per
+// query tile a P V half whose P has long been ready sits behind the same warp's Q K^T (measured: ~1,000 clk from "P half
+// ready" to its issue) and the score tile is interleaved with the other tile's P V; here a ready MMA of one kind never
+// waits behind the issue of the other kind.  Same barriers and phases as mmaIssuerWarp; both roles see every K/V slot
+// full before they hand it back (commit by the role that multiplied with it, plain arrive by the other).
+// ------------------------------------------------------------------------------------------------
+template <int D, int STAGES, int DT>
+__device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p, const int role) {
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);
+    using L = SmemLayout<D, STAGES>;
+    constexpr uint32_t kFmt = (DT == kBF16) ? 1u : 0u;
+    constexpr uint32_t idesc_qk = umma_idesc(kBlockM, kBlockN, kFmt, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc(kBlockM, D, kFmt, 0, 1);
+    const uint32_t bar0 = smem_base + L::kBarOff;
+    auto bar = [&](int i) { return bar0 + 8u * uint32_t(i); };
+    const uint64_t desc_k_major = umma_desc_sw128(0, 16, 1024);
+    const uint64_t desc_mn_major = umma_desc_sw128(0, kHalfBytes, 1024);
+    const uint32_t s_tmem = tmem_base + kTmemS;
+
+    auto slot_addr = [&](int it) { return smem_base + L::kKVOff + (it % STAGES) * L::kKVTileBytes; };
+    auto empty_bar = [&](int it) { return bar(L::kBarKVEmpty + it % STAGES); };
+    auto wait_full = [&](int it) {
+        mbar_wait(bar(L::kBarKVFull + it % STAGES), (it / STAGES) & 1);
+        tc_fence_after();
+    };
+    auto arrive = [&](uint32_t b) { if (elect_one_sync()) mbar_arrive(b); __syncwarp(); };
+
+    int it0 = 0, kq = 0, sq = 0;
+    int st[2] = {0, 0}, ko[2] = {0, 0};
+    for (int k = 0;; ++k) {
+        const int item = fetch_item<D, STAGES>(smem_base, k);
+        if (item < 0) break;
+        const WorkItem w = decode_item(p, item);
+        const int n = w.n_kv;
+        if (n <= 0) continue;
+        const int nts[2] = {w.n_tile0, w.n_tile1};
+
+        if (role == 0) {
+            // ---- every Q_t K_j^T, in the order of the shared S buffer: S_0(0), S_1(0), S_0(1), ...
+            mbar_wait(bar(L::kBarQFull), kq & 1);
+            ++kq;
+            for (int j = 0; j < n; ++j) {
+                wait_full(it0 + 2 * j);
+                const uint32_t k_smem = slot_addr(it0 + 2 * j);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int idx = (t == 0) ? sq + j - 1 : sq + j;     // predecessor in the buffer: S_1(j-1) / S_0(j)
+                    if (idx >= 0) {
+                        mbar_wait(bar(L::kBarSFree + (1 - t)), idx & 1);
+                        tc_fence_after();
+                    }
+                    if (elect_one_sync()) {
+                        if (j < nts[t]) {
+                            const uint64_t a0 = desc_k_major + ((smem_base + L::kQOff + t * L::kQTileBytes) >> 4);
+                            const uint64_t b0 = desc_k_major + (k_smem >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < D / 16; ++ks) {
+                                const uint32_t off = ((ks / 4) * kHalfBytes + (ks % 4) * 32) >> 4;
+                                umma_ss(s_tmem, a0 + off, b0 + off, idesc_qk, ks > 0);
+                            }
+                            tc_commit(bar(L::kBarSFull + t));
+                        } else {
+                            mbar_arrive_n(bar(L::kBarSFree + t), kSoftmaxThreadsPerTile);   // virtual step: pass the buffer on
+                        }
+                    }
+                    __syncwarp();
+                }
+                // K_j and (after the item's last step) the Q tiles go back once every Q K^T issued so far has retired
+                if (elect_one_sync()) {
+                    tc_commit(empty_bar(it0 + 2 * j));
+                    if (j + 1 == n) tc_commit(bar(L::kBarQEmpty));
+                }
+                __syncwarp();
+                wait_full(it0 + 2 * j + 1);                  // V_j: not ours, but the slot's phases must be seen in order
+                arrive(empty_bar(it0 + 2 * j + 1));
+            }
+        } else {
+            // ---- every P_t V_j, in the order the P halves arrive: P_0 first half, P_0 second half, P_1 first, P_1 second
+            for (int j = 0; j < n; ++j) {
+                wait_full(it0 + 2 * j);                      // K_j: not ours
+                arrive(empty_bar(it0 + 2 * j));
+                wait_full(it0 + 2 * j + 1);
+                const uint64_t b0 = desc_mn_major + (slot_addr(it0 + 2 * j + 1) >> 4);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (j >= nts[t]) continue;
+                    const uint32_t ph = (st[t] + j) & 1;
+                    const uint32_t p_tmem = tmem_base + tmem_p_col(t);
+                    const uint32_t o_tmem = tmem_base + kTmemO0 + 128u * t;
+                    if (j == 0 && ko[t] > 0) mbar_wait(bar(L::kBarOFree + t), (ko[t] - 1) & 1);   // previous item's epilogue has read O_t
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        mbar_wait(bar(L::kBarPFull + 2 * t + half), ph);
+                        tc_fence_after();
+                        if (elect_one_sync()) {
+#pragma unroll
+                            for (int kk = 0; kk < kBlockN / 32; ++kk) {
+                                const int ks = half * (kBlockN / 32) + kk;
+                                umma_ts(o_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+                            }
+                            if (half == 1) tc_commit(bar(L::kBarOFull + t));
+                            else if (kSplitOFull<D>) tc_commit(bar(L::kBarOHalf + t));
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (elect_one_sync()) tc_commit(empty_bar(it0 + 2 * j + 1));   // V_j back once every P V issued so far has retired
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            st[t] += nts[t];
+            ko[t] += nts[t] > 0 ? 1 : 0;
+        }
+        sq += n;
+        it0 += 2 * n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Softmax warpgroup for query tile t (128 threads, one score row each), including the lazy O rescale and the
 // epilogue (O/l -> global, optional LSE).  Persistent: loops over the published work items; the epilogue of one item
 // overlaps the next item's first Q K^T.

@@ -64,6 +64,16 @@ constexpr int kEmuPairsPer8 = FA_EMU_PAIRS_PER_8;
 template <int D>
 constexpr bool kSplitOFull = (FA_SPLIT_OFULL != 0) && D == 128;
 
+// The two MMA issuer warps are split by type at d = 128 (all Q K^T / all P V, mmaTypeIssuerWarp) and by query tile at
+// d = 64 (mmaIssuerWarp).  By type, measured against by tile on the shipped build: 2,672 -> 2,645 clk per step causal 8K,
+// 2,613 -> 2,598 non-causal, 3,055 -> 2,949 causal 2K; +0.1 .. +0.9 % wall clock held under the power cap; at d = 64
+// 2,559 -> 2,612 (worse: the P V there is too short to be worth a warp of its own).
+#ifndef FA_ISSUER_BY_TYPE
+#define FA_ISSUER_BY_TYPE 1
+#endif
+template <int D>
+constexpr bool kIssuerByType = (FA_ISSUER_BY_TYPE != 0) && D == 128;
+
 struct FwdParams {
     void* O;                 // output, same dtype as Q
     float* lse;              // optional [B, Hq, Nq] log-sum-exp (natural log), may be null
