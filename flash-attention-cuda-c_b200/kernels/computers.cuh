@@ -148,19 +148,25 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
             mbar_wait(bar(L::kBarPFull + 2 * t), ph);
             tc_fence_after();
             FA_PROF_MARK(2);             // waiting for P
+            FA_TRACE_EV(p.prof, k, t, 1, j, 2);
             issue_pv_half(slot_addr(it0 + 2 * j + 1), j > 0, 0, 0);
+            FA_TRACE_EV(p.prof, k, t, 1, j, 3);
             FA_PROF_MARK(3);             // issue + bookkeeping
             mbar_wait(bar(L::kBarPFull + 2 * t + 1), ph);
             tc_fence_after();
             FA_PROF_MARK(2);
+            FA_TRACE_EV(p.prof, k, t, 1, j, 4);
             issue_pv_half(slot_addr(it0 + 2 * j + 1), j > 0, 1, empty_bar(it0 + 2 * j + 1));
+            FA_TRACE_EV(p.prof, k, t, 1, j, 5);
             FA_PROF_MARK(3);
         };
         auto qk = [&](int j) {
             FA_PROF_MARK(3);
             wait_s_buffer(j);
             FA_PROF_MARK(4);             // waiting for the shared S buffer
+            FA_TRACE_EV(p.prof, k, t, 1, j, 0);
             issue_qk(slot_addr(it0 + 2 * j), empty_bar(it0 + 2 * j), j + 1 == nt);
+            FA_TRACE_EV(p.prof, k, t, 1, j, 1);
             FA_PROF_MARK(3);
         };
 
@@ -252,6 +258,7 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
                         mbar_wait(bar(L::kBarSFree + (1 - t)), idx & 1);
                         tc_fence_after();
                     }
+                    FA_TRACE_EV(p.prof, k, t, 1, j, 0);
                     if (elect_one_sync()) {
                         if (j < nts[t]) {
                             const uint64_t a0 = desc_k_major + ((smem_base + L::kQOff + t * L::kQTileBytes) >> 4);
@@ -267,6 +274,7 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
                         }
                     }
                     __syncwarp();
+                    FA_TRACE_EV(p.prof, k, t, 1, j, 1);
                 }
                 // K_j and (after the item's last step) the Q tiles go back once every Q K^T issued so far has retired
                 if (elect_one_sync()) {
@@ -295,6 +303,7 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
                     for (int half = 0; half < 2; ++half) {
                         mbar_wait(bar(L::kBarPFull + 2 * t + half), ph);
                         tc_fence_after();
+                        FA_TRACE_EV(p.prof, k, t, 1, j, 2 + 2 * half);
                         if (elect_one_sync()) {
 #pragma unroll
                             for (int kk = 0; kk < kBlockN / 32; ++kk) {
@@ -305,6 +314,7 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
                             else if (kSplitOFull<D>) tc_commit(bar(L::kBarOHalf + t));
                         }
                         __syncwarp();
+                        FA_TRACE_EV(p.prof, k, t, 1, j, 3 + 2 * half);
                     }
                 }
                 if (elect_one_sync()) tc_commit(empty_bar(it0 + 2 * j + 1));   // V_j back once every P V issued so far has retired
@@ -366,9 +376,11 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
         for (int j = 0; j < n; ++j) {
             const uint32_t ph = (st + j) & 1;
             FA_PROF_MARK(5);             // loop overhead / l update / epilogue
+            FA_TRACE_EV(p.prof, k, t, 0, j, 5);
             mbar_wait(s_full, ph);
             tc_fence_after();
             FA_PROF_MARK(0);             // waiting for S
+            FA_TRACE_EV(p.prof, k, t, 0, j, 0);
 
             uint32_t r[kBlockN];
 #pragma unroll
@@ -376,6 +388,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             tc_wait_ld();
             tc_fence_before();
             mbar_arrive(s_free);         // the score row is in registers: the shared S buffer may be overwritten
+            FA_TRACE_EV(p.prof, k, t, 0, j, 1);
 #ifdef FA_PHASE_PROFILE
             // lag between the two warpgroups: clocks since the OTHER warpgroup last took an S tile (warp 0 of each reports)
             if ((threadIdx.x & 127) == 0) {
@@ -464,6 +477,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 mbar_wait(kSplitOFull<D> ? o_half : o_full, ph ^ 1);
                 tc_fence_after();
             }
+            FA_TRACE_EV(p.prof, k, t, 0, j, 2);
             {
                 uint32_t pk[32];
                 exp_quarter(0, pk);
@@ -476,6 +490,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 tc_wait_st();                      // first half landed while quarter 2 was computed
                 tc_fence_before();
                 mbar_arrive(p_full0);              // MMA may start P V on keys 0..63
+                FA_TRACE_EV(p.prof, k, t, 0, j, 3);
                 exp_quarter(3, pk + 16);
                 if (kSplitOFull<D> && j > 0) {
                     mbar_wait(o_full, ph ^ 1);
@@ -487,6 +502,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(p_full1);
+            FA_TRACE_EV(p.prof, k, t, 0, j, 4);
             FA_PROF_MARK(4);             // store drain + arrive
 
             l_run += (s0.x + s0.y) + (s1.x + s1.y);

@@ -36,6 +36,20 @@
 #define FA_PROF_FLUSH(ptr, base, n)
 #endif
 
+// FA_TRACE builds: CTA 0 timestamps the hand-offs of a few 128-key steps of its second work item into the debug profile
+// buffer (scripts/trace_steps.py prints the timeline): slot = 64 + ((tile * 2 + role) * 16 + (j - 8)) * 8 + event, role 0 =
+// softmax warpgroup (events: got S, released S, exponentials start, first / second P half delivered, ready for S),
+// role 1 = MMA issue (Q K^T issue begins / ends, first P V half begins / ends, second half begins / ends)
+#ifdef FA_TRACE
+#define FA_TRACE_EV(prof, k, tile, role, j, ev)                                                                  \
+    do {                                                                                                            \
+        if ((prof) && blockIdx.x == 0 && (k) == 1 && (j) >= 8 && (j) < 24 && (threadIdx.x & 31) == 0)               \
+            (prof)[64 + (((tile) * 2 + (role)) * 16 + ((j) - 8)) * 8 + (ev)] = (unsigned long long)clock64();       \
+    } while (0)
+#else
+#define FA_TRACE_EV(prof, k, tile, role, j, ev)
+#endif
+
 namespace fa {
 
 enum DType : int { kF32 = 0, kF16 = 1, kBF16 = 2 };

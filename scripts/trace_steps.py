@@ -1,4 +1,5 @@
-"""trace_steps.py [B H N d causal] — timeline of the hand-offs inside CTA 0 (FA_TRACE build, variants/libfa_v_TRACE.so or FA_LIB):
+"""trace_steps.py [B H N d causal] — timeline of the hand-offs inside CTA 0 (FA_TRACE build: scripts/build_variants.sh TRACE
+"-DFA_TRACE" -> variants/libfa_v_TRACE.so, or FA_LIB):
 per 128-key step j = 8..23 of the CTA's second work item, when each softmax warpgroup got its S tile, freed the buffer,
 started its exponentials and delivered the two halves of P, and when each MMA issuer issued Q K^T and the two halves of
 P V.  Times in clocks relative to the first traced event."""
