@@ -32,9 +32,10 @@ namespace fa {
 // of one (batch, head), claimed from a global atomic counter (LPT order inside a head, (batch, head)-major overall).
 //   warps 0-3  softmax + correction + epilogue for query tile 0
 //   warps 4-7  softmax + correction + epilogue for query tile 1
-//   warp  8    MMA issuer for query tile 0
+//   warp  8    MMA issuer: every Q K^T (d = 128) / everything of query tile 0 (d = 64)
 //   warp  9    TMA producer + scheduler (one thread)
-//   warp 10    TMEM allocator, then MMA issuer for query tile 1
+//   warp 10    TMEM allocator, then MMA issuer: every P V (d = 128) / everything of query tile 1 (d = 64)
+//   warp 11    idle (times the CTA for scripts/cycles.py when a debug profile buffer is set)
 // ------------------------------------------------------------------------------------------------
 template <int D, int STAGES, int DT, bool OVEC32>
 __global__ void __launch_bounds__(kNumThreads, 1)

@@ -30,9 +30,9 @@ constexpr int kHalfBytes = kBlockN * 128;   // 16 KiB: one half of a 128-row til
 // Warp roles (384 threads = 3 warpgroups)
 constexpr int kSoftmaxWarps = 8;   // warps 0-3: query tile 0, warps 4-7: query tile 1; one full score row (128 columns) per thread
 constexpr int kSoftmaxThreadsPerTile = kSoftmaxWarps * 32 / kTilesPerCta;   // arrivals per query tile on s_free / o_free
-constexpr int kMmaWarp0 = kSoftmaxWarps;           // MMA issuer of query tile 0
+constexpr int kMmaWarp0 = kSoftmaxWarps;           // MMA issuer: every Q K^T (d = 128) / query tile 0 (d = 64)
 constexpr int kLoadWarp = kSoftmaxWarps + 1;       // TMA producer + scheduler (one thread)
-constexpr int kMmaWarp1 = kSoftmaxWarps + 2;       // MMA issuer of query tile 1; also allocates / frees TMEM
+constexpr int kMmaWarp1 = kSoftmaxWarps + 2;       // MMA issuer: every P V (d = 128) / query tile 1 (d = 64); also allocates / frees TMEM
 constexpr int kTmemWarp = kMmaWarp1;
 constexpr int kNumThreads = (kSoftmaxWarps + 4) * 32;
 // Register split (setmaxnreg): 168 per thread at launch -> 256 x 216 (softmax, no spills) + 128 x 72 (MMA issuers / TMA
