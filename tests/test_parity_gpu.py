@@ -83,9 +83,12 @@ def test_16bit_ragged_lengths(n, causal):
 
 @pytest.mark.parametrize("nq,nk", [(128, 512), (100, 1000), (512, 128), (300, 200), (1, 777)])
 @pytest.mark.parametrize("causal", [False, True])
-def test_16bit_nq_ne_nk(nq, nk, causal):
-    # bottom-right aligned causal mask; with Nq > Nk the first rows see no key -> zeros, lse = -inf
-    _check(*_inputs(1, 2, 2, nq, nk, 64, torch.bfloat16, seed=nq + nk), causal=causal)
+@pytest.mark.parametrize("d", [64, 128])
+def test_16bit_nq_ne_nk(nq, nk, causal, d):
+    # bottom-right aligned causal mask; with Nq > Nk the first rows see no key -> zeros, lse = -inf.  Both head dims: the
+    # MMA issuers are split by query tile at d = 64 and by type at d = 128, and a query tile without any visible key tile
+    # (virtual steps on the shared score buffer) takes a different path in each
+    _check(*_inputs(1, 2, 2, nq, nk, d, torch.bfloat16, seed=nq + nk), causal=causal)
 
 
 @pytest.mark.parametrize("hq,hkv", [(8, 1), (8, 2), (6, 3), (64, 8)])
