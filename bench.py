@@ -24,8 +24,20 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: whatever NCCL has to say (NCCL_DEBUG=VERSION / INFO) goes to stderr
+# stdout carries exactly one JSON line: whatever NCCL has to say (NCCL_DEBUG=INFO through its logger, NCCL_DEBUG=VERSION
+# through a bare printf) goes to stderr — file descriptor 1 points at stderr until the line is printed (emit()).
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "flash-attention-cuda-c_b200")
@@ -140,7 +152,7 @@ def run_reference(args, wl):
             "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -285,7 +297,7 @@ def run_ours(args, wl, wl_name):
                            "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "wall_s_timed_region": t_wall, "kernel_ms_min": min(kernel_ms), "kernel_ms_max": max(kernel_ms)}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
