@@ -384,8 +384,24 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             FA_TRACE_EV(p.prof, k, t, 0, j, 0);
 
             uint32_t r[kBlockN];
+            const int kv0 = j * kBlockN;
+            const bool need_mask = (kv0 + kBlockN > p.Nk) || (p.causal && (kv0 + kBlockN - 1 > tile_row0 + p.causal_off));
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            // first half of the row, then the second half in flight while the first half's row max is computed (-0.4 % cycles)
+            tmem_ld32(tS, r);
+            tmem_ld32(tS + 32u, r + 32);
+            tc_wait_ld();
+            tmem_ld32(tS + 64u, r + 64);
+            tmem_ld32(tS + 96u, r + 96);
+            if (!need_mask) {
 #pragma unroll
-            for (int q = 0; q < kBlockN / 32; ++q) tmem_ld32(tS + 32u * q, r + 32 * q);
+                for (int cc = 0; cc < kBlockN / 2; cc += 8) {
+                    mx0 = max3(mx0, __uint_as_float(r[cc + 0]), __uint_as_float(r[cc + 1]));
+                    mx1 = max3(mx1, __uint_as_float(r[cc + 2]), __uint_as_float(r[cc + 3]));
+                    mx2 = max3(mx2, __uint_as_float(r[cc + 4]), __uint_as_float(r[cc + 5]));
+                    mx3 = max3(mx3, __uint_as_float(r[cc + 6]), __uint_as_float(r[cc + 7]));
+                }
+            }
             tc_wait_ld();
             tc_fence_before();
             mbar_arrive(s_free);         // the score row is in registers: the shared S buffer may be overwritten
@@ -402,8 +418,6 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
 #endif
             FA_PROF_MARK(1);             // tcgen05.ld of the score row
 
-            const int kv0 = j * kBlockN;
-            const bool need_mask = (kv0 + kBlockN > p.Nk) || (p.causal && (kv0 + kBlockN - 1 > tile_row0 + p.causal_off));
             if (need_mask) {
                 const int lim_c = p.causal ? (row + p.causal_off) : 0x7fffffff;
                 const int lim = min(lim_c, p.Nk - 1) - kv0;   // columns c > lim are masked
@@ -411,9 +425,17 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 for (int cc = 0; cc < kBlockN; ++cc) r[cc] = mask_gt(r[cc], cc, lim);   // -inf where cc > lim
             }
 
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            if (need_mask) {             // the first half's maxima were not taken before the mask was applied
 #pragma unroll
-            for (int cc = 0; cc < kBlockN; cc += 8) {
+                for (int cc = 0; cc < kBlockN / 2; cc += 8) {
+                    mx0 = max3(mx0, __uint_as_float(r[cc + 0]), __uint_as_float(r[cc + 1]));
+                    mx1 = max3(mx1, __uint_as_float(r[cc + 2]), __uint_as_float(r[cc + 3]));
+                    mx2 = max3(mx2, __uint_as_float(r[cc + 4]), __uint_as_float(r[cc + 5]));
+                    mx3 = max3(mx3, __uint_as_float(r[cc + 6]), __uint_as_float(r[cc + 7]));
+                }
+            }
+#pragma unroll
+            for (int cc = kBlockN / 2; cc < kBlockN; cc += 8) {
                 mx0 = max3(mx0, __uint_as_float(r[cc + 0]), __uint_as_float(r[cc + 1]));
                 mx1 = max3(mx1, __uint_as_float(r[cc + 2]), __uint_as_float(r[cc + 3]));
                 mx2 = max3(mx2, __uint_as_float(r[cc + 4]), __uint_as_float(r[cc + 5]));
