@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-line
               "-shared", "-Xcompiler", "-fPIC"]
 
 FA_DTYPE_F32, FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1, 2
-EXPORTS = ["fa_fwd", "fa_fwd_strided", "fa_fwd_carry", "fa_mha_fwd_f32", "fa_fwd_host", "fa_merge_partial", "fa_cast_out",
+EXPORTS = ["fa_fwd", "fa_fwd_strided", "fa_fwd_carry", "fa_fwd_carry_window", "fa_mha_fwd_f32", "fa_fwd_host", "fa_merge_partial", "fa_cast_out",
            "fa_set_sm_reserve", "fa_device_info", "fa_block_q", "fa_block_kv", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
 
 _lib = None
@@ -60,6 +60,7 @@ def lib() -> ctypes.CDLL:
         L.fa_fwd.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, vp]
         L.fa_fwd_strided.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, ctypes.POINTER(ll), vp]
         L.fa_fwd_carry.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, ctypes.POINTER(ll), vp]
+        L.fa_fwd_carry_window.argtypes = [vp, vp, vp, vp, vp] + [ip] * 9 + [fl, ip, ctypes.POINTER(ll), vp]
         L.fa_mha_fwd_f32.argtypes = [vp, vp, vp, vp] + [ip] * 4 + [fl, ip, vp]
         L.fa_fwd_host.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip]
         L.fa_merge_partial.argtypes = [vp, vp, vp, vp, ll, ip, ip, vp]
@@ -167,20 +168,24 @@ def merge_partial(acc_o, acc_lse, part_o, part_lse):
     _check(rc, "fa_merge_partial")
 
 
-def attention_forward_carry(q, k, v, acc_o, acc_lse, causal=False, scale=None):
+def attention_forward_carry(q, k, v, acc_o, acc_lse, causal=False, scale=None, row_offset=0):
     """Ring step: fold attention(q, k, v) over this key range into the fp32 running (acc_o, acc_lse) pair, in place.
-    q [B,Hq,Nq,d], k/v [B,Hkv,Nk,d] may be strided views (last dim contiguous); acc_o / acc_lse must be contiguous."""
+    q [B,Hq,Nq,d], k/v [B,Hkv,Nk,d] may be strided views (last dim contiguous); acc_o [B,Hq,R,d] / acc_lse [B,Hq,R] must be
+    contiguous with R >= Nq: q's rows are the accumulator's rows [row_offset, row_offset + Nq)."""
     import torch
     B, Hq, Nq, d = q.shape
     _, Hkv, Nk, _ = k.shape
     if not (acc_o.is_contiguous() and acc_lse.is_contiguous() and acc_o.dtype == torch.float32):
         raise FaError("acc_o / acc_lse must be contiguous fp32")
+    R = acc_o.shape[2]
+    if acc_o.shape != (B, Hq, R, d) or acc_lse.shape != (B, Hq, R):
+        raise FaError("acc_o / acc_lse shape mismatch")
     strides = (ctypes.c_longlong * 9)(*(list(q.stride()[:3]) + list(k.stride()[:3]) + list(v.stride()[:3])))
     with torch.cuda.device(q.device):
-        rc = lib().fa_fwd_carry(q.data_ptr(), k.data_ptr(), v.data_ptr(), acc_o.data_ptr(), acc_lse.data_ptr(),
-                                B, Hq, Hkv, Nq, Nk, d, _dtype_code(q), float(scale) if scale else 0.0,
-                                int(bool(causal)), strides, _stream_ptr(q))
-    _check(rc, "fa_fwd_carry")
+        rc = lib().fa_fwd_carry_window(q.data_ptr(), k.data_ptr(), v.data_ptr(), acc_o.data_ptr(), acc_lse.data_ptr(), R, int(row_offset),
+                                       B, Hq, Hkv, Nq, Nk, d, _dtype_code(q), float(scale) if scale else 0.0,
+                                       int(bool(causal)), strides, _stream_ptr(q))
+    _check(rc, "fa_fwd_carry_window")
 
 
 def set_sm_reserve(sms: int):

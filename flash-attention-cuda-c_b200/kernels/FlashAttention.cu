@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -71,8 +72,29 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // [B, H, N, d] tensor with element strides (sb, sh, sn, 1); box = 64 columns x 128 rows, 128B swizzle.
+// Encoding a map is a pure function of (base, dtype, shape, strides), so the last few are kept per host thread: a caller
+// that launches the same tensors again (a decode loop, a benchmark, a CUDA-graph-less training step) pays the three driver
+// calls once.  Launch-bound shapes (BASELINE configs[1]: one 20 us kernel) are where this shows.
+struct MapKey {
+    const void* base; int dtype, B, H, N, d; long long sb, sh, sn;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && dtype == o.dtype && B == o.B && H == o.H && N == o.N && d == o.d && sb == o.sb && sh == o.sh && sn == o.sn;
+    }
+};
+struct MapCache {
+    static constexpr int kEntries = 24;
+    MapKey key[kEntries] = {};
+    CUtensorMap map[kEntries];
+    bool valid[kEntries] = {};
+    unsigned next = 0;
+};
+thread_local MapCache g_maps;
+
 int make_tile_map(CUtensorMap* m, const void* base, int dtype, int B, int H, int N, int d, long long sb, long long sh,
                   long long sn) {
+    const MapKey key{base, dtype, B, H, N, d, sb, sh, sn};
+    for (int i = 0; i < MapCache::kEntries; ++i)
+        if (g_maps.valid[i] && g_maps.key[i] == key) { *m = g_maps.map[i]; return FA_OK; }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     const CUtensorMapDataType dt = dtype == FA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -86,28 +108,68 @@ int make_tile_map(CUtensorMap* m, const void* base, int dtype, int B, int H, int
     CUresult r = enc(m, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    const unsigned slot = g_maps.next++ % MapCache::kEntries;
+    g_maps.key[slot] = key; g_maps.map[slot] = *m; g_maps.valid[slot] = true;
     return FA_OK;
 }
 
 // ---- work-item counters for the persistent kernel ------------------------------------------------------
-// One zeroed int per launch, taken round-robin from a per-device pool (so launches in flight on different streams do
-// not share a counter as long as fewer than kCounterSlots of them overlap).
-constexpr int kCounterSlots = 1024;
+// The kernel's dynamic scheduler needs one int that is zero when the launch starts.  The kernel leaves it zero itself (the
+// CTA that makes the launch's last claim resets it, loaders.cuh), so there is no per-launch memset; what the host has to
+// guarantee is that two launches that may be in flight at the same time never share a counter:
+//   * eager launches: one counter per (device, stream) — launches on one stream are serialised by the stream;
+//     cudaStreamPerThread names a different stream in every host thread, so it gets a counter per thread;
+//   * launches recorded into a CUDA graph: a counter of their own each (a replay runs on whatever stream the graph is
+//     launched on, possibly beside eager launches on the stream it was captured from), never reused.
+// Counters come from zero-filled chunks that are never freed (4 bytes per stream / captured launch).
+struct CounterPool {
+    static constexpr int kChunk = 4096;
+    std::mutex mu;
+    std::unordered_map<cudaStream_t, int*> by_stream;
+    int* chunk = nullptr;
+    int used = kChunk;
+    int sms = 0;
+    cudaStream_t helper = nullptr;
+    // next zeroed int of the pool; mu held.  Safe while some stream of this thread is capturing (relaxed capture mode for
+    // the allocation; the fill runs on a private non-blocking stream).
+    int* take() {
+        if (used == kChunk) {
+            cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+            cudaThreadExchangeStreamCaptureMode(&mode);
+            int* c = nullptr;
+            bool ok = cudaMalloc(&c, kChunk * sizeof(int)) == cudaSuccess;
+            if (ok && !helper) ok = cudaStreamCreateWithFlags(&helper, cudaStreamNonBlocking) == cudaSuccess;
+            ok = ok && cudaMemsetAsync(c, 0, kChunk * sizeof(int), helper) == cudaSuccess && cudaStreamSynchronize(helper) == cudaSuccess;
+            cudaThreadExchangeStreamCaptureMode(&mode);
+            if (!ok) return nullptr;
+            chunk = c;
+            used = 0;
+        }
+        return chunk + used++;
+    }
+};
+CounterPool g_counters[64];
+
 int* next_counter(cudaStream_t st, int* sm_count_out) {
-    static std::mutex mu;
-    static int* pool[64] = {};
-    static int sms[64] = {};
-    static unsigned next[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!pool[dev]) {
-        if (cudaMalloc(&pool[dev], kCounterSlots * sizeof(int)) != cudaSuccess) return nullptr;
-        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    CounterPool& pool = g_counters[dev];
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(pool.mu);
+    if (!pool.sms) cudaDeviceGetAttribute(&pool.sms, cudaDevAttrMultiProcessorCount, dev);
+    *sm_count_out = pool.sms;
+    if (cap != cudaStreamCaptureStatusNone) return pool.take();
+    if (st == cudaStreamPerThread) {
+        thread_local int* mine[64] = {};
+        if (!mine[dev]) mine[dev] = pool.take();
+        return mine[dev];
     }
-    int* c = pool[dev] + (next[dev]++ % kCounterSlots);
-    if (cudaMemsetAsync(c, 0, sizeof(int), st) != cudaSuccess) return nullptr;
-    *sm_count_out = sms[dev];
+    if (st == cudaStreamLegacy) st = nullptr;
+    auto it = pool.by_stream.find(st);
+    if (it != pool.by_stream.end()) return it->second;
+    int* c = pool.take();
+    if (c) pool.by_stream.emplace(st, c);
     return c;
 }
 
@@ -143,7 +205,7 @@ int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
     int max_ctas = sm_count - g_sm_reserve.load();      // SMs left free for a concurrent communication kernel
     if (max_ctas < 1) max_ctas = 1;
     const int grid = p.total_items < max_ctas ? p.total_items : max_ctas;   // persistent: one CTA per SM
-    kern<<<grid, fa::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
+    kern<<<grid, fa::KCfg<D>::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
     g_launches.fetch_add(1);
     FA_CUDA(cudaGetLastError());
     return FA_OK;
@@ -169,10 +231,13 @@ int launch_fp32(const fa::Fp32Params& p, cudaStream_t st) {
 
 int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, int B, int Hq, int Hkv, int Nq, int Nk,
              int d, int dtype, float scale, int causal, const long long* s, cudaStream_t st,
-             float* acc_o = nullptr, float* acc_lse = nullptr) {
+             float* acc_o = nullptr, float* acc_lse = nullptr, int acc_rows = 0, int acc_off = 0) {
     const bool carry = acc_o != nullptr;
     if (carry && (!acc_lse || dtype == FA_DTYPE_F32)) return fail(FA_ERR_INVALID_ARGUMENT, "carry mode needs acc_lse and a 16-bit dtype");
     if (carry) O = acc_o;   // only used for the null / alignment checks below
+    if (carry && acc_rows == 0) acc_rows = Nq;
+    if (carry && (acc_off < 0 || acc_rows < Nq || acc_off > acc_rows - Nq))
+        return fail(FA_ERR_INVALID_ARGUMENT, "carry window [%d, %d) does not fit %d accumulator rows", acc_off, acc_off + Nq, acc_rows);
     if (!Q || !K || !V || !O) return fail(FA_ERR_INVALID_ARGUMENT, "null tensor pointer");
     if (B <= 0 || Hq <= 0 || Hkv <= 0 || Nq <= 0 || Nk <= 0 || d <= 0)
         return fail(FA_ERR_INVALID_ARGUMENT, "non-positive size (B=%d Hq=%d Hkv=%d Nq=%d Nk=%d d=%d)", B, Hq, Hkv, Nq, Nk, d);
@@ -227,7 +292,7 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     if (int rc = make_tile_map(&tv, V, dtype, B, Hkv, Nk, d, s[6], s[7], s[8])) return rc;
 
     fa::FwdParams p;
-    p.O = O; p.lse = lse; p.acc_o = acc_o; p.acc_lse = acc_lse; p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
+    p.O = O; p.lse = lse; p.acc_o = acc_o; p.acc_lse = acc_lse; p.acc_rows = acc_rows; p.acc_off = acc_off; p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
     p.o_stride_b = s[9]; p.o_stride_h = s[10]; p.o_stride_n = s[11];
     p.scale = sc; p.scale_log2 = sc * 1.4426950408889634f;
     p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
@@ -244,16 +309,16 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     return bf ? launch_sm100<64, 8, fa::kBF16, false>(tq, tk, tv, p, st) : launch_sm100<64, 8, fa::kF16, false>(tq, tk, tv, p, st);
 }
 
-// ---- host-buffer pipeline state ---------------------------------------------------------------------
+// ---- host-buffer pipeline state: one per device, each behind its own lock ------------------------------
 struct HostPipe {
     static constexpr int kSlots = 3;
+    std::mutex mu;
     cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
     void* buf[kSlots] = {nullptr, nullptr, nullptr};
     size_t cap[kSlots] = {0, 0, 0};
-    int device = -1;
+    bool ready = false;
 };
-std::mutex g_pipe_mu;
-HostPipe g_pipe;
+HostPipe g_pipes[64];
 
 }  // namespace
 
@@ -297,6 +362,20 @@ int fa_fwd_carry(const void* Q, const void* K, const void* V, float* acc_o, floa
     return fwd_impl(Q, K, V, nullptr, nullptr, B, Hq, Hkv, Nq, Nk, d, dtype, scale, causal, s, (cudaStream_t)stream, acc_o, acc_lse);
 }
 
+int fa_fwd_carry_window(const void* Q, const void* K, const void* V, float* acc_o, float* acc_lse, int acc_rows, int acc_row_offset,
+                        int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype, float scale, int causal,
+                        const long long* qkv_strides, void* stream) {
+    g_err[0] = 0;
+    if (!acc_o || !acc_lse) return fail(FA_ERR_INVALID_ARGUMENT, "acc_o / acc_lse is null");
+    long long s[12];
+    const long long qs[3] = {(long long)Hq * Nq * d, (long long)Nq * d, d};
+    const long long ks[3] = {(long long)Hkv * Nk * d, (long long)Nk * d, d};
+    for (int i = 0; i < 3; ++i) { s[i] = qs[i]; s[3 + i] = ks[i]; s[6 + i] = ks[i]; s[9 + i] = qs[i]; }
+    if (qkv_strides) for (int i = 0; i < 9; ++i) s[i] = qkv_strides[i];
+    return fwd_impl(Q, K, V, nullptr, nullptr, B, Hq, Hkv, Nq, Nk, d, dtype, scale, causal, s, (cudaStream_t)stream, acc_o, acc_lse,
+                    acc_rows, acc_row_offset);
+}
+
 int fa_mha_fwd_f32(const float* Q, const float* K, const float* V, float* O, int batchSize, int numHeads, int seqLen,
                    int d_head, float scale, int is_causal, void* stream) {
     g_err[0] = 0;
@@ -324,33 +403,30 @@ int fa_fwd_host(const void* hQ, const void* hK, const void* hV, void* hO, float*
     if (upc > 65535) upc = 65535;
     const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)d);
 
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
     int dev = 0;
     FA_CUDA(cudaGetDevice(&dev));
-    if (g_pipe.device != dev) {
-        for (int i = 0; i < HostPipe::kSlots; ++i) {
-            if (g_pipe.buf[i]) cudaFree(g_pipe.buf[i]);
-            if (g_pipe.streams[i]) cudaStreamDestroy(g_pipe.streams[i]);
-            g_pipe.buf[i] = nullptr; g_pipe.cap[i] = 0; g_pipe.streams[i] = nullptr;
-        }
-        for (int i = 0; i < HostPipe::kSlots; ++i) FA_CUDA(cudaStreamCreateWithFlags(&g_pipe.streams[i], cudaStreamNonBlocking));
-        g_pipe.device = dev;
+    if (dev < 0 || dev >= 64) return fail(FA_ERR_INVALID_ARGUMENT, "device index %d out of range", dev);
+    HostPipe& pipe = g_pipes[dev];
+    // one call at a time per device (the staging buffers are the device's); calls on different devices run side by side
+    std::lock_guard<std::mutex> lk(pipe.mu);
+    if (!pipe.ready) {
+        for (int i = 0; i < HostPipe::kSlots; ++i) FA_CUDA(cudaStreamCreateWithFlags(&pipe.streams[i], cudaStreamNonBlocking));
+        pipe.ready = true;
     }
     const size_t need = (size_t)upc * unit_bytes + 1024;
     for (int i = 0; i < HostPipe::kSlots; ++i) {
-        if (g_pipe.cap[i] < need) {
-            if (g_pipe.buf[i]) FA_CUDA(cudaFree(g_pipe.buf[i]));
-            g_pipe.buf[i] = nullptr; g_pipe.cap[i] = 0;
-            FA_CUDA(cudaMalloc(&g_pipe.buf[i], need));
-            g_pipe.cap[i] = need;
+        if (pipe.cap[i] < need) {
+            if (pipe.buf[i]) FA_CUDA(cudaFree(pipe.buf[i]));
+            pipe.buf[i] = nullptr; pipe.cap[i] = 0;
+            FA_CUDA(cudaMalloc(&pipe.buf[i], need));
+            pipe.cap[i] = need;
         }
     }
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-    int slot = 0;
-    for (long long u0 = 0; u0 < units; u0 += upc, slot = (slot + 1) % HostPipe::kSlots) {
-        const long long nu = (units - u0 < upc) ? (units - u0) : upc;
-        cudaStream_t st = g_pipe.streams[slot];
-        char* base = (char*)g_pipe.buf[slot];
+    // one chunk: H2D of its Q/K/V units, the kernel, D2H of O (and LSE), all on the chunk's stream
+    auto run_chunk = [&](long long u0, long long nu, int slot) -> int {
+        cudaStream_t st = pipe.streams[slot];
+        char* base = (char*)pipe.buf[slot];
         char* dQ = base;
         char* dK = dQ + al(nu * q_unit);
         char* dV = dK + al(nu * kv_unit);
@@ -363,9 +439,17 @@ int fa_fwd_host(const void* hQ, const void* hK, const void* hV, void* hO, float*
         if (int rc = fwd_impl(dQ, dK, dV, dO, dL, (int)nu, g, 1, Nq, Nk, d, dtype, sc, causal, nullptr, st)) return rc;
         FA_CUDA(cudaMemcpyAsync((char*)hO + u0 * q_unit, dO, nu * q_unit, cudaMemcpyDeviceToHost, st));
         if (hlse) FA_CUDA(cudaMemcpyAsync((char*)hlse + u0 * lse_unit, dL, nu * lse_unit, cudaMemcpyDeviceToHost, st));
+        return FA_OK;
+    };
+    int rc = FA_OK, slot = 0;
+    for (long long u0 = 0; u0 < units && rc == FA_OK; u0 += upc, slot = (slot + 1) % HostPipe::kSlots)
+        rc = run_chunk(u0, (units - u0 < upc) ? (units - u0) : upc, slot);
+    // drain every stream before returning, also on failure: earlier chunks may still be copying into the caller's buffers
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(pipe.streams[i]);
+        if (e != cudaSuccess && rc == FA_OK) rc = fail(FA_ERR_CUDA, "cudaStreamSynchronize -> %s", cudaGetErrorString(e));
     }
-    for (int i = 0; i < HostPipe::kSlots; ++i) FA_CUDA(cudaStreamSynchronize(g_pipe.streams[i]));
-    return FA_OK;
+    return rc;
 }
 
 int fa_merge_partial(float* acc_o, float* acc_lse, const void* part_o, const float* part_lse, long long rows, int d,

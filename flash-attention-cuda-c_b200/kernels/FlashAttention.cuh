@@ -28,20 +28,22 @@
 namespace fa {
 
 // ------------------------------------------------------------------------------------------------
-// B200 kernel: persistent, grid = min(#SMs, work items), 384 threads, 1 CTA / SM; a work item is a 256-row query block
-// of one (batch, head), claimed from a global atomic counter (LPT order inside a head, (batch, head)-major overall).
-//   warps 0-3  softmax + correction + epilogue for query tile 0
-//   warps 4-7  softmax + correction + epilogue for query tile 1
-//   warp  8    MMA issuer: every Q K^T (d = 128) / everything of query tile 0 (d = 64)
-//   warp  9    TMA producer + scheduler (one thread)
-//   warp 10    TMEM allocator, then MMA issuer: every P V (d = 128) / everything of query tile 1 (d = 64)
-//   warp 11    idle (times the CTA for scripts/cycles.py when a debug profile buffer is set)
+// B200 kernel: persistent, grid = min(#SMs, work items), 1 CTA / SM; a work item is a 256-row query block of one
+// (batch, head), claimed from a global atomic counter (LPT order inside a head, (batch, head)-major overall).
+// With S = KCfg<D>::kSoftmaxWarps (8 or 16) softmax warps the CTA has S + 4 warps:
+//   warps 0 .. S/2-1   softmax + correction + epilogue for query tile 0
+//   warps S/2 .. S-1   softmax + correction + epilogue for query tile 1
+//   warp  S      MMA issuer: every Q K^T (d = 128) / everything of query tile 0 (d = 64)
+//   warp  S+1    TMA producer + scheduler (one thread)
+//   warp  S+2    TMEM allocator, then MMA issuer: every P V (d = 128) / everything of query tile 1 (d = 64)
+//   warp  S+3    idle (times the CTA for scripts/cycles.py when a debug profile buffer is set)
 // ------------------------------------------------------------------------------------------------
 template <int D, int STAGES, int DT, bool OVEC32>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(KCfg<D>::kNumThreads, 1)
 fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
     using L = SmemLayout<D, STAGES>;
+    using C = KCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0) __trap();        // SWIZZLE_128B tiles need 1024-B alignment; see SmemLayout::kDynamicBytes
@@ -51,7 +53,7 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int warp = threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
 
-    if (warp == kMmaWarp0 && lane == 0) {
+    if (warp == C::kMmaWarp0 && lane == 0) {
         const uint32_t bar0 = smem_base + L::kBarOff;
         mbar_init(bar0 + 8 * L::kBarQFull, 1);
         mbar_init(bar0 + 8 * L::kBarQEmpty, kIssuerByType<D> ? 1 : 2); // both MMA issuers (split by type: the Q K^T issuer alone)
@@ -61,21 +63,21 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar0 + 8 * (L::kBarSFull + t), 1);
-            mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t), 128);
-            mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t + 1), 128);
+            mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t), C::kSoftmaxThreadsPerTile);
+            mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t + 1), C::kSoftmaxThreadsPerTile);
             mbar_init(bar0 + 8 * (L::kBarOFull + t), 1);
-            mbar_init(bar0 + 8 * (L::kBarOFree + t), kSoftmaxThreadsPerTile);
+            mbar_init(bar0 + 8 * (L::kBarOFree + t), C::kSoftmaxThreadsPerTile);
             mbar_init(bar0 + 8 * (L::kBarSchedFull + t), 1);
-            mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 2 + kSoftmaxWarps);   // both MMA issuers + every softmax warp
-            mbar_init(bar0 + 8 * (L::kBarSFree + t), kSoftmaxThreadsPerTile);
+            mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 2 + C::kSoftmaxWarps);   // both MMA issuers + every softmax warp
+            mbar_init(bar0 + 8 * (L::kBarSFree + t), C::kSoftmaxThreadsPerTile);
             mbar_init(bar0 + 8 * (L::kBarOHalf + t), 1);
         }
         fence_mbar_init();
-    } else if (warp == kLoadWarp && lane == 0) {
+    } else if (warp == C::kLoadWarp && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
-    } else if (warp == kTmemWarp) {
+    } else if (warp == C::kTmemWarp) {
         tmem_alloc(smem_base + L::kTmemPtrOff, kTmemCols);
         tmem_relinquish();
     }
@@ -86,31 +88,32 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // Cycle counter for A/B work (fa_debug_set_profile_buffer): the otherwise idle last warp times the CTA from here to the
     // final barrier; prof[30] = max over CTAs, prof[31] = sum.  Wall-clock A/B on a power-capped GPU is too noisy.
     long long cta_t0 = 0;
-    if (p.prof != nullptr && threadIdx.x == kNumThreads - 32) cta_t0 = clock64();
+    if (p.prof != nullptr && threadIdx.x == C::kNumThreads - 32) cta_t0 = clock64();
 
-    if (warp < kSoftmaxWarps) {
-        reg_inc<kSoftmaxRegs>();
-        softmaxWarpgroup<D, STAGES, DT, OVEC32>(smem_base, tmem_base, p, warp / 4);
+    if (warp < C::kSoftmaxWarps) {
+        reg_inc<C::kSoftmaxRegs>();
+        if constexpr (C::kRows16) softmaxRows16<D, STAGES, DT, OVEC32>(smem_base, tmem_base, p, warp / 8, (warp / 4) & 1);
+        else softmaxWarpgroup<D, STAGES, DT, OVEC32>(smem_base, tmem_base, p, warp / 4);
     } else {
-        reg_dec<kOtherRegs>();
-        if (warp == kMmaWarp0) {
+        reg_dec<C::kOtherRegs>();
+        if (warp == C::kMmaWarp0) {
             if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 0);
             else mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 0);
-        } else if (warp == kMmaWarp1) {
+        } else if (warp == C::kMmaWarp1) {
             if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 1);
             else mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 1);
-        } else if (warp == kLoadWarp) {
+        } else if (warp == C::kLoadWarp) {
             if (lane == 0) tmaLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, p);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == kTmemWarp) {
+    if (warp == C::kTmemWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
-    if (p.prof != nullptr && threadIdx.x == kNumThreads - 32) {
+    if (p.prof != nullptr && threadIdx.x == C::kNumThreads - 32) {
         const unsigned long long dt = (unsigned long long)(clock64() - cta_t0);
         atomicMax(p.prof + 30, dt);
         atomicAdd(p.prof + 31, dt);

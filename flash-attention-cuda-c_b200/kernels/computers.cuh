@@ -138,7 +138,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
         };
         auto virtual_qk = [&](int j) {
             wait_s_buffer(j);
-            if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), kSoftmaxThreadsPerTile);
+            if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), KCfg<D>::kSoftmaxThreadsPerTile);
             __syncwarp();
         };
         auto pv = [&](int j) {
@@ -271,7 +271,7 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
                             }
                             tc_commit(bar(L::kBarSFull + t));
                         } else {
-                            mbar_arrive_n(bar(L::kBarSFree + t), kSoftmaxThreadsPerTile);   // virtual step: pass the buffer on
+                            mbar_arrive_n(bar(L::kBarSFree + t), KCfg<D>::kSoftmaxThreadsPerTile);   // virtual step: pass the buffer on
                         }
                     }
                     __syncwarp();
@@ -579,8 +579,9 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             // carry mode (ring-KV step): fold this call's partial result over its key range into the fp32 running
             // (output, log-sum-exp) pair:  lse' = log(e^lse_acc + e^lse_part),  O' = O_acc e^(lse_acc-lse') + (O/l) e^(lse_part-lse')
             float wa = 1.f, wp = 0.f, lse_new = -INFINITY;
+            const long long acc_lin = ((long long)w.b * p.Hq + w.h) * p.acc_rows + p.acc_off + row;
             if (row_ok) {
-                const float lse_acc = p.acc_lse[row_lin];
+                const float lse_acc = p.acc_lse[acc_lin];
                 const float mx = fmaxf(lse_acc, lse_part);
                 lse_new = mx;
                 if (mx != -INFINITY) {
@@ -594,7 +595,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             if (n > 0) {
                 mbar_wait(o_full, (st + n - 1) & 1);
                 tc_fence_after();
-                float* arow = p.acc_o + row_lin * D;
+                float* arow = p.acc_o + acc_lin * D;
 #pragma unroll
                 for (int q = 0; q < D / 32; ++q) {
                     uint32_t o[32];
@@ -615,11 +616,330 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 tc_fence_before();
                 mbar_arrive(o_free);
             }
-            if (row_ok && n > 0) p.acc_lse[row_lin] = lse_new;
+            if (row_ok && n > 0) p.acc_lse[acc_lin] = lse_new;
         }
         st += n;
     }
     if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 0, 6);
+    tc_fence_before();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Softmax, 16-warp layout (KCfg<D>::kRows16).  Warp (t, h, q) serves query tile t, TMEM lane quarter q (= its SM
+// sub-partition), rows [32q + 16h, 32q + 16h + 16) of the tile: the two warps of a quarter split its rows, so nothing but the
+// epilogue's (1/l, lse) pair ever crosses between warps.  Scores are read with tcgen05.ld 16x256b — thread (quad rr = lane/4,
+// c4 = lane%4) holds rows rr and rr + 8 of the warp's 16, columns 8g + 2 c4 + {0,1} of every 8-column group g: 2 x 32 scores
+// per thread and tile instead of 1 x 128 — so a row max costs two quad shuffles, the row sum stays a per-thread partial until
+// the epilogue, and the packed P pairs of a thread are exactly one tcgen05.st 16x128b fragment.  Each SM sub-partition then
+// runs FOUR softmax warps (two per query tile): while one sits in a MUFU.EX2 (8 clk, during which a warp issues nothing else)
+// the other three issue their FFMA2 / FADD2 / F2FP / FMNMX3 / TMEM traffic.  Barriers, phases and the hand-offs with the MMA
+// issuers are those of softmaxWarpgroup (arrival counts 256 per query tile instead of 128).
+// Epilogue: the same two warps switch to the 32x32b view (one row per lane) and split the COLUMNS of the quarter's 32 rows,
+// so every lane still stores contiguous 64- or 128-byte pieces of one output row; 1/l and the log-sum-exp of a row come from
+// the thread that owned it during the key loop through 2 KB of shared memory and a 64-thread named barrier.
+// ------------------------------------------------------------------------------------------------
+template <int D, int STAGES, int DT, bool OVEC32>
+__device__ __forceinline__ void softmaxRows16(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, const int t, const int h) {
+    using L = SmemLayout<D, STAGES>;
+    uint32_t bar0 = smem_base + L::kBarOff;
+    asm volatile("" : "+r"(bar0));     // keep in a register
+    const uint32_t s_full = bar0 + 8u * (L::kBarSFull + t);
+    const uint32_t p_full0 = bar0 + 8u * (L::kBarPFull + 2 * t);
+    const uint32_t p_full1 = p_full0 + 8u;
+    const uint32_t o_full = bar0 + 8u * (L::kBarOFull + t);
+    const uint32_t o_free = bar0 + 8u * (L::kBarOFree + t);
+    const uint32_t s_free = bar0 + 8u * (L::kBarSFree + t);
+    const uint32_t o_half = bar0 + 8u * (L::kBarOHalf + t);
+
+    const int q4 = (threadIdx.x / 32) & 3;     // TMEM lane quarter (and SM sub-partition) of this warp
+    const int lane = threadIdx.x & 31;
+    const int c4 = lane & 3, rr = lane >> 2;
+    const int r_in_tile = q4 * 32 + h * 16 + rr;               // first of this thread's two rows inside the query tile; the other is + 8
+    const uint32_t lane16 = uint32_t(q4 * 32 + h * 16) << 16;  // 16-lane window of the key loop
+    const uint32_t lane32 = uint32_t(q4 * 32) << 16;           // 32-lane window of the epilogue
+    uint32_t tS = tmem_base + lane16 + kTmemS;
+    uint32_t tP = tmem_base + lane16 + tmem_p_col(t);
+    uint32_t tO = tmem_base + lane16 + kTmemO0 + 128u * t;
+    const float c = p.scale_log2;
+    asm volatile("" : "+r"(tS), "+r"(tP), "+r"(tO));
+    const uint32_t exch = smem_base + L::kExchOff + uint32_t(t * kBlockM) * 8u;
+
+    int st = 0;      // key tiles this query tile has processed so far (barrier phase bookkeeping)
+    for (int k = 0;; ++k) {
+        const int item = fetch_item<D, STAGES>(smem_base, k);
+        if (item < 0) break;
+        int n, j_mask;     // key tiles of this query tile; first key tile that needs the causal / tail mask (kept instead of the item's coordinates)
+        {
+            const WorkItem w = decode_item(p, item);
+            n = w.n_tile(t);
+            const int tile_row0 = w.q0 + t * kBlockM;
+            // tail: kv0 + 128 > Nk  <=>  j >= Nk / 128;   causal: kv0 + 127 > tile_row0 + off  <=>  128 j > tile_row0 + off - 127
+            j_mask = p.Nk / kBlockN;
+            if (p.causal) {
+                const int x = tile_row0 + p.causal_off - (kBlockN - 1);
+                const int jc = x < 0 ? 0 : x / kBlockN + 1;
+                j_mask = jc < j_mask ? jc : j_mask;
+            }
+        }
+
+        float mA = -INFINITY, mB = -INFINITY;            // max in use per row, raw (unscaled) score units
+        float2 lA = make_float2(0.f, 0.f), lB = make_float2(0.f, 0.f);   // this thread's share of the two row sums
+
+        for (int j = 0; j < n; ++j) {
+            const uint32_t ph = (st + j) & 1;
+            mbar_wait(s_full, ph);
+            tc_fence_after();
+
+            uint32_t r[kBlockN / 2];
+            const int kv0 = j * kBlockN;
+            const bool need_mask = j >= j_mask;
+            float a0 = -INFINITY, a1 = -INFINITY, b0 = -INFINITY, b1 = -INFINITY;
+            tmem_ld_16x256b_x8(tS, r);                   // keys 0..63
+            tc_wait_ld();
+            tmem_ld_16x256b_x8(tS + 64u, r + 32);        // keys 64..127 in flight while the first half's maxima are taken
+            if (!need_mask) {
+#pragma unroll
+                for (int g = 0; g < 8; g += 2) {
+                    a0 = max3(a0, __uint_as_float(r[4 * g + 0]), __uint_as_float(r[4 * g + 1]));
+                    b0 = max3(b0, __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                    a1 = max3(a1, __uint_as_float(r[4 * g + 4]), __uint_as_float(r[4 * g + 5]));
+                    b1 = max3(b1, __uint_as_float(r[4 * g + 6]), __uint_as_float(r[4 * g + 7]));
+                }
+            }
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(s_free);         // the scores are in registers: the shared S buffer may be overwritten
+
+            if (need_mask) {
+                // column of r[4g + 2*row + e] is 8g + 2 c4 + e: masked iff 8g + e > lim(row) - 2 c4
+                const int rowA = decode_item(p, item).q0 + t * kBlockM + r_in_tile;
+                const int limA_c = p.causal ? (rowA + p.causal_off) : 0x7fffffff;
+                const int limB_c = p.causal ? (rowA + 8 + p.causal_off) : 0x7fffffff;
+                const int limA = min(limA_c, p.Nk - 1) - kv0 - 2 * c4;
+                const int limB = min(limB_c, p.Nk - 1) - kv0 - 2 * c4;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    r[4 * g + 0] = mask_gt(r[4 * g + 0], 8 * g, limA);
+                    r[4 * g + 1] = mask_gt(r[4 * g + 1], 8 * g + 1, limA);
+                    r[4 * g + 2] = mask_gt(r[4 * g + 2], 8 * g, limB);
+                    r[4 * g + 3] = mask_gt(r[4 * g + 3], 8 * g + 1, limB);
+                }
+#pragma unroll
+                for (int g = 0; g < 8; g += 2) {
+                    a0 = max3(a0, __uint_as_float(r[4 * g + 0]), __uint_as_float(r[4 * g + 1]));
+                    b0 = max3(b0, __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                    a1 = max3(a1, __uint_as_float(r[4 * g + 4]), __uint_as_float(r[4 * g + 5]));
+                    b1 = max3(b1, __uint_as_float(r[4 * g + 6]), __uint_as_float(r[4 * g + 7]));
+                }
+            }
+#pragma unroll
+            for (int g = 8; g < 16; g += 2) {
+                a0 = max3(a0, __uint_as_float(r[4 * g + 0]), __uint_as_float(r[4 * g + 1]));
+                b0 = max3(b0, __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                a1 = max3(a1, __uint_as_float(r[4 * g + 4]), __uint_as_float(r[4 * g + 5]));
+                b1 = max3(b1, __uint_as_float(r[4 * g + 6]), __uint_as_float(r[4 * g + 7]));
+            }
+            // a row lives in the 4 threads of a quad
+            float mxA = fmaxf(a0, a1), mxB = fmaxf(b0, b1);
+            mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 1));
+            mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 1));
+            mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 2));
+            mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 2));
+            const float nA = fmaxf(mxA, mA), nB = fmaxf(mxB, mB);
+
+            if (j == 0) {
+                mA = nA;
+                mB = nB;
+            } else {
+                // lazy rescale: (new - old) is NaN when both are -inf -> compares false
+                const bool gA = (nA - mA) * c > kRescaleThreshold, gB = (nB - mB) * c > kRescaleThreshold;
+                if (__any_sync(0xffffffffu, gA || gB)) {
+                    const float fA = gA ? ex2_approx((mA - nA) * c) : 1.0f;
+                    const float fB = gB ? ex2_approx((mB - nB) * c) : 1.0f;
+                    mbar_wait(o_full, ph ^ 1);      // P V of the previous key tile has retired
+                    tc_fence_after();
+                    // 16 columns at a time: the path is rare and must not cost the key loop any registers
+#pragma unroll 1
+                    for (int ch = 0; ch < D / 16; ++ch) {
+                        uint32_t o[8];
+                        tmem_ld_16x256b_x2(tO + 16u * ch, o);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            o[4 * g + 0] = __float_as_uint(__uint_as_float(o[4 * g + 0]) * fA);
+                            o[4 * g + 1] = __float_as_uint(__uint_as_float(o[4 * g + 1]) * fA);
+                            o[4 * g + 2] = __float_as_uint(__uint_as_float(o[4 * g + 2]) * fB);
+                            o[4 * g + 3] = __float_as_uint(__uint_as_float(o[4 * g + 3]) * fB);
+                        }
+                        tmem_st_16x256b_x2(tO + 16u * ch, o);
+                    }
+                    lA.x *= fA; lA.y *= fA;
+                    lB.x *= fB; lB.y *= fB;
+                    if (gA) mA = nA;
+                    if (gB) mB = nB;
+                }
+            }
+            const float msA = (mA == -INFINITY) ? 0.f : mA, msB = (mB == -INFINITY) ? 0.f : mB;
+            const float2 c2 = make_float2(c, c);
+            const float2 nmA = make_float2(-msA * c, -msA * c), nmB = make_float2(-msB * c, -msB * c);
+
+            // exp2 of one score pair (both of the same row): MUFU.EX2 for most pairs, FMA-pipe emulation for kEmuPairsPer8 of 8
+            auto exp_pair = [&](int i, const float2& nm) -> float2 {
+                float2 x = fma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, nm);
+                if (((i / 2) % 8) * 3 % 8 < kEmuPairsPer8) {
+                    x = ex2_emu2(x);
+                } else {
+                    x.x = ex2_approx(x.x);
+                    x.y = ex2_approx(x.y);
+                }
+                return x;
+            };
+            // groups [g0, g0 + ng) of 8 keys -> 2 packed columns each, written IN PLACE over the first half of the registers
+            // the scores came from (packed column 2g + e replaces r[2g + e], which group g / 2 has already consumed), so
+            // that the block the tcgen05.st reads needs no registers of its own: at 104 registers per thread there are none
+            auto exp_groups = [&](int g0, int ng) {
+#pragma unroll
+                for (int g = g0; g < g0 + ng; ++g) {
+                    const float2 xA = exp_pair(4 * g, nmA), xB = exp_pair(4 * g + 2, nmB);
+                    lA = add2(lA, xA);
+                    lB = add2(lB, xB);
+                    const int o = (g < 8) ? 2 * g : 32 + 2 * (g - 8);
+                    r[o + 0] = pack16<DT>(xA.x, xA.y);
+                    r[o + 1] = pack16<DT>(xB.x, xB.y);
+                }
+            };
+            // P_t V_{j-1} (its first half, with the split wait) must have retired before the P columns are overwritten
+            if (j > 0) {
+                mbar_wait(kSplitOFull<D> ? o_half : o_full, ph ^ 1);
+                tc_fence_after();
+            }
+            exp_groups(0, 8);
+            tmem_st_16x128b_x8(tP, r);             // keys 0..63 of P
+            exp_groups(8, 4);
+            tc_wait_st();                          // first half landed while the third quarter was computed
+            tc_fence_before();
+            mbar_arrive(p_full0);                  // MMA may start P V on keys 0..63
+            exp_groups(12, 4);
+            if (kSplitOFull<D> && j > 0) {
+                mbar_wait(o_full, ph ^ 1);
+                tc_fence_after();
+            }
+            tmem_st_16x128b_x8(tP + 32u, r + 32);  // keys 64..127 of P
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(p_full1);
+        }
+
+        // ---- epilogue: 32x32b view, this warp stores columns [h D/2, (h+1) D/2) of the quarter's 32 rows ----
+        constexpr int HC = D / 2;
+        const WorkItem w = decode_item(p, item);
+        const int tile_row0 = w.q0 + t * kBlockM;
+        const int rowA = tile_row0 + r_in_tile;
+        const int row = tile_row0 + q4 * 32 + lane;
+        const bool row_ok = row < p.Nq;
+        const long long bh_lin = (long long)w.b * p.Hq + w.h;
+        const long long row_lin = bh_lin * p.Nq + row;
+        const bool carry = p.acc_o != nullptr;
+        float2 mine = make_float2(0.f, -INFINITY);     // plain: (1/l, lse) of `row`; carry: (weight of the running O, weight of this call's unnormalised O)
+        if (n > 0) {
+            float sA = lA.x + lA.y, sB = lB.x + lB.y;
+            sA += __shfl_xor_sync(0xffffffffu, sA, 1);
+            sB += __shfl_xor_sync(0xffffffffu, sB, 1);
+            sA += __shfl_xor_sync(0xffffffffu, sA, 2);
+            sB += __shfl_xor_sync(0xffffffffu, sB, 2);
+            if (c4 == 0) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float l_run = e ? sB : sA, m_run = e ? mB : mA;
+                    const float m_fin = (m_run == -INFINITY) ? 0.f : m_run;
+                    const float lse_part = (l_run > 0.f) ? (m_fin * p.scale + logf(l_run)) : -INFINITY;
+                    float2 v = make_float2((l_run > 0.f) ? 1.0f / l_run : 0.f, lse_part);
+                    if (carry) {
+                        // fold into the running log-sum-exp here, by the one thread that owns the row:
+                        //   lse' = log(e^lse_acc + e^lse_part),  O' = O_acc e^(lse_acc-lse') + (O/l) e^(lse_part-lse')
+                        const int orow_e = rowA + 8 * e;
+                        float wa = 1.f, wp = 0.f;
+                        if (orow_e < p.Nq) {
+                            const long long lin = bh_lin * p.acc_rows + p.acc_off + orow_e;
+                            const float lse_acc = p.acc_lse[lin];
+                            const float mx = fmaxf(lse_acc, lse_part);
+                            if (mx != -INFINITY) {
+                                const float ea = expf(lse_acc - mx), ep = expf(lse_part - mx);
+                                const float inv = 1.0f / (ea + ep);
+                                wa = ea * inv;
+                                wp = ep * inv * v.x;
+                                p.acc_lse[lin] = mx + logf(ea + ep);
+                            }
+                        }
+                        v = make_float2(wa, wp);
+                    }
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(exch + uint32_t(r_in_tile + 8 * e) * 8u), "f"(v.x), "f"(v.y) : "memory");
+                }
+            }
+            named_bar_sync(1u + uint32_t(t * 4 + q4), 64u);     // the two warps of this (tile, quarter)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(mine.x), "=f"(mine.y) : "r"(exch + uint32_t(q4 * 32 + lane) * 8u) : "memory");
+        }
+        const uint32_t tO32 = tmem_base + lane32 + kTmemO0 + 128u * t + uint32_t(HC * h);
+        if (!carry) {
+            const float inv_l = mine.x;
+            uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)w.b * p.o_stride_b + (long long)w.h * p.o_stride_h +
+                             (long long)row * p.o_stride_n + HC * h;
+            if (n > 0) {
+                mbar_wait(o_full, (st + n - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int qq = 0; qq < HC / 16; ++qq) {       // 16 columns = one 32-byte sector of the row at a time
+                    uint32_t o[16];
+                    tmem_ld16(tO32 + 16u * qq, o);
+                    tc_wait_ld();
+                    uint32_t hh[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        hh[i] = pack16<DT>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+                    if (row_ok) {
+                        if constexpr (OVEC32) {
+                            st_global_v8(orow + 16 * qq, hh);
+                        } else {
+                            st_global_v4(orow + 16 * qq, hh[0], hh[1], hh[2], hh[3]);
+                            st_global_v4(orow + 16 * qq + 8, hh[4], hh[5], hh[6], hh[7]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(o_free);         // O columns may be overwritten by the next item's first P V
+            } else if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < HC / 8; ++i) st_global_v4(orow + 8 * i, 0u, 0u, 0u, 0u);
+            }
+            if (p.lse != nullptr && row_ok && h == 0) p.lse[row_lin] = mine.y;
+        } else if (n > 0) {
+            // carry mode (ring-KV step): O_acc <- O_acc * wa + O * wp on this warp's half of the columns
+            const float wa = mine.x, wp = mine.y;
+            mbar_wait(o_full, (st + n - 1) & 1);
+            tc_fence_after();
+            float* arow = p.acc_o + (bh_lin * p.acc_rows + p.acc_off + row) * D + HC * h;
+#pragma unroll
+            for (int qq = 0; qq < HC / 16; ++qq) {
+                uint32_t o[16];
+                tmem_ld16(tO32 + 16u * qq, o);
+                tc_wait_ld();
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 a = ld_global_f4(arow + 16 * qq + 4 * i);
+                        a.x = a.x * wa + __uint_as_float(o[4 * i + 0]) * wp;
+                        a.y = a.y * wa + __uint_as_float(o[4 * i + 1]) * wp;
+                        a.z = a.z * wa + __uint_as_float(o[4 * i + 2]) * wp;
+                        a.w = a.w * wa + __uint_as_float(o[4 * i + 3]) * wp;
+                        st_global_f4(arow + 16 * qq + 4 * i, a);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(o_free);
+        }
+        st += n;
+    }
     tc_fence_before();
 }
 

@@ -27,25 +27,46 @@ constexpr int kBlockN = 128;       // key/value rows per tile
 constexpr int kHalfCols = 64;      // columns per swizzle-128B half (64 x 2 B = 128 B)
 constexpr int kHalfBytes = kBlockN * 128;   // 16 KiB: one half of a 128-row tile
 
-// Warp roles (384 threads = 3 warpgroups)
-constexpr int kSoftmaxWarps = 8;   // warps 0-3: query tile 0, warps 4-7: query tile 1; one full score row (128 columns) per thread
-constexpr int kSoftmaxThreadsPerTile = kSoftmaxWarps * 32 / kTilesPerCta;   // arrivals per query tile on s_free / o_free
-constexpr int kMmaWarp0 = kSoftmaxWarps;           // MMA issuer: every Q K^T (d = 128) / query tile 0 (d = 64)
-constexpr int kLoadWarp = kSoftmaxWarps + 1;       // TMA producer + scheduler (one thread)
-constexpr int kMmaWarp1 = kSoftmaxWarps + 2;       // MMA issuer: every P V (d = 128) / query tile 1 (d = 64); also allocates / frees TMEM
-constexpr int kTmemWarp = kMmaWarp1;
-constexpr int kNumThreads = (kSoftmaxWarps + 4) * 32;
-// Register split (setmaxnreg): 168 per thread at launch -> 256 x 216 (softmax, no spills) + 128 x 72 (MMA issuers / TMA
-// producer); the CTA may not hold more than the 384 x 168 it was launched with.
-#ifndef FA_SOFTMAX_REGS
-#define FA_SOFTMAX_REGS 216
-#define FA_OTHER_REGS 72
+// Warp roles.  The softmax side comes in two layouts, chosen per head dim at compile time (KCfg<D>):
+//   8 softmax warps  (384 threads): warps 0-3 query tile 0, warps 4-7 query tile 1; one full score row (128 columns) per
+//                    thread (tcgen05.ld 32x32b), row max / row sum need no shuffles (softmaxWarpgroup)
+//   16 softmax warps (640 threads): 8 warps per query tile; the two warps that share a TMEM lane quarter split its 32 rows
+//                    16 / 16 (tcgen05.ld 16x256b: a row is spread over the 4 threads of a quad, 2 x 32 scores per thread),
+//                    so every SM sub-partition runs FOUR softmax warps and the MUFU time of one overlaps the FMA / ALU / TMEM
+//                    instructions of the others (softmaxRows16).  A lone warp cannot overlap its own MUFU.EX2 with anything
+//                    (8.14 clk per MUFU + its other instructions, scripts/microbench/pipes.cu), which is what bounds the
+//                    8-warp layout at ~2,600 clk per pair of 128-key tiles against 2,048 clk of MMAs.
+#ifndef FA_SM_WARPS_D128
+#define FA_SM_WARPS_D128 16
 #endif
-constexpr int kSoftmaxRegs = FA_SOFTMAX_REGS;
-constexpr int kOtherRegs = FA_OTHER_REGS;
-constexpr int kLaunchRegs = (65536 / kNumThreads) / 8 * 8;     // what __launch_bounds__(kNumThreads, 1) gives every thread
-static_assert(kSoftmaxWarps * 32 * kSoftmaxRegs + 128 * kOtherRegs <= kNumThreads * kLaunchRegs,
-              "register split exceeds what the CTA owns at launch");
+#ifndef FA_SM_WARPS_D64
+#define FA_SM_WARPS_D64 16
+#endif
+template <int D>
+struct KCfg {
+    static constexpr int kSoftmaxWarps = (D == 128) ? FA_SM_WARPS_D128 : FA_SM_WARPS_D64;
+    static_assert(kSoftmaxWarps == 8 || kSoftmaxWarps == 16, "8 or 16 softmax warps");
+    static constexpr bool kRows16 = kSoftmaxWarps == 16;
+    static constexpr int kSoftmaxThreadsPerTile = kSoftmaxWarps * 32 / kTilesPerCta;   // arrivals per query tile on s_free / p_full / o_free
+    static constexpr int kMmaWarp0 = kSoftmaxWarps;           // MMA issuer: every Q K^T (by type) / query tile 0 (by tile)
+    static constexpr int kLoadWarp = kSoftmaxWarps + 1;       // TMA producer + scheduler (one thread)
+    static constexpr int kMmaWarp1 = kSoftmaxWarps + 2;       // MMA issuer: every P V (by type) / query tile 1 (by tile); also allocates / frees TMEM
+    static constexpr int kTmemWarp = kMmaWarp1;
+    static constexpr int kNumThreads = (kSoftmaxWarps + 4) * 32;
+    // Register split (setmaxnreg): what __launch_bounds__(kNumThreads, 1) gives every thread at launch is re-divided between
+    // the softmax warps and the rest; the CTA may not hold more than it was launched with.
+    //   8 warps : 168 at launch -> 256 x 216 + 128 x 72;   16 warps: 96 at launch -> 512 x 104 + 128 x 64
+    static constexpr int kLaunchRegs = (65536 / kNumThreads) / 8 * 8;
+#ifdef FA_SOFTMAX_REGS
+    static constexpr int kSoftmaxRegs = FA_SOFTMAX_REGS;
+    static constexpr int kOtherRegs = FA_OTHER_REGS;
+#else
+    static constexpr int kSoftmaxRegs = kRows16 ? 104 : 216;
+    static constexpr int kOtherRegs = kRows16 ? 64 : 72;
+#endif
+    static_assert(kSoftmaxWarps * 32 * kSoftmaxRegs + 128 * kOtherRegs <= kNumThreads * kLaunchRegs,
+                  "register split exceeds what the CTA owns at launch");
+};
 // Of every 8 consecutive score pairs, this many take the FMA-pipe exp2 (ex2_emu2) instead of MUFU.EX2.
 #ifndef FA_EMU_PAIRS_PER_8
 #define FA_EMU_PAIRS_PER_8 0
@@ -79,6 +100,7 @@ struct FwdParams {
     float* lse;              // optional [B, Hq, Nq] log-sum-exp (natural log), may be null
     float* acc_o;            // carry mode (ring-KV steps): fp32 [B, Hq, Nq, d] running output, updated in place; O is not written
     float* acc_lse;          // carry mode: fp32 [B, Hq, Nq] running log-sum-exp, updated in place
+    int acc_rows, acc_off;   // carry mode: the running pair has acc_rows (>= Nq) rows per (batch, head); this call's query row i is its row acc_off + i
     int B, Hq, Hkv, Nq, Nk;
     long long o_stride_b, o_stride_h, o_stride_n;   // in elements; innermost (d) stride is 1
     float scale;             // softmax scale (1/sqrt(d) by default)
@@ -88,7 +110,7 @@ struct FwdParams {
     int q_heads_per_kv;      // Hq / Hkv
     int num_q_blocks;        // 256-row query blocks per (batch, head)
     int total_items;         // B * Hq * num_q_blocks work items
-    int* sched_counter;      // device int, zero at launch: next work item = gridDim.x + atomicAdd(counter, 1)
+    int* sched_counter;      // device int, zero at launch and left zero by the launch: next work item = gridDim.x + atomicAdd(counter, 1)
     unsigned long long* prof; // FA_PHASE_PROFILE builds only: per-phase cycle counters (see scripts/phase_profile.py)
 };
 
@@ -115,7 +137,12 @@ struct SmemLayout {
     static constexpr int kNumBars = kBarOHalf + 2;
     static constexpr int kSchedItemOff = kBarOff + kNumBars * 8;   // int[2]
     static constexpr int kTmemPtrOff = kSchedItemOff + 8;
-    static constexpr int kBytes = kTmemPtrOff + 16;
+    // 16-softmax-warp layout only: per query tile and row, (1 / row sum, log-sum-exp) handed from the warp that owns the row
+    // in the 16-lane layout to the warp that stores it in the epilogue (float2[2][128])
+    static constexpr int kExchOff = kTmemPtrOff + 16;
+    static constexpr int kExchBytes = KCfg<D>::kRows16 ? kTilesPerCta * kBlockM * 8 : 0;
+    static constexpr int kBytes = kExchOff + kExchBytes;
+    static_assert(kBytes <= 232448, "more than 227 KB of shared memory");
     // The dynamic shared-memory window of a kernel without static shared memory starts 1024-B aligned (the kernel traps if
     // it ever does not), so no alignment slack is reserved.
     static constexpr int kDynamicBytes = kBytes;
@@ -221,7 +248,12 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
                 }
             }
         }
-        item = int(gridDim.x) + atomicAdd(p.sched_counter, 1);
+        // Claim the next item.  Every CTA keeps claiming until a claim fails, so a launch makes exactly total_items claims;
+        // whoever makes the last one (no other claim can follow) puts the counter back to zero for the next launch that uses
+        // it — the host never has to clear it (no memset node per launch).
+        const int claimed = atomicAdd(p.sched_counter, 1);
+        if (claimed == p.total_items - 1) atomicExch(p.sched_counter, 0);
+        item = int(gridDim.x) + claimed;
     }
     // Tail: wait until the consumer has handed back the last fills, so that no tcgen05.commit arrive is still in
     // flight towards this CTA's shared memory when the CTA exits.

@@ -263,6 +263,68 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 }
 
 // ------------------------------------------------------------------------------------------
+// tcgen05.ld / tcgen05.st, 16-lane shapes: the warp addresses 16 TMEM lanes (the lane field of taddr is the first one and must
+// lie inside the warp's own 32-lane quarter, so two warps of the same quarter can each own 16 rows of a tile).
+//   16x256b.xN : thread t holds, per repetition g (8 columns): regs 4g+{0,1} = lane t/4,     columns 8g + 2(t%4) + {0,1}
+//                                                              regs 4g+{2,3} = lane t/4 + 8, same columns
+//                (the accumulator fragment of mma.sync: a row is spread over the 4 threads of a quad)
+//   16x128b.xN : per repetition g (4 columns): reg 2g = lane t/4, column 4g + t%4; reg 2g+1 = lane t/4 + 8, same column
+//                (what the packed 16-bit pairs of a 16x256b fragment become: column 4g + t%4 = keys 8g + 2(t%4) + {0,1})
+// ------------------------------------------------------------------------------------------
+#define FA_R8(r, o) "=r"(r[o]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7])
+#define FA_W8(r, o) "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {   // 64 columns -> 32 registers
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : FA_R8(r, 0), FA_R8(r, 8), FA_R8(r, 16), FA_R8(r, 24)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {   // 32 columns -> 16 registers
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : FA_R8(r, 0), FA_R8(r, 8)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), FA_W8(r, 0), FA_W8(r, 8)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* r) {   // 16 columns -> 8 registers
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : FA_R8(r, 0) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), FA_W8(r, 0) : "memory");
+}
+// 32x32b.x16: thread i <-> lane (lane_base + i), 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : FA_R8(r, 0), FA_R8(r, 8)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x128b_x8(uint32_t taddr, const uint32_t* r) {   // 32 columns <- 16 registers
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), FA_W8(r, 0), FA_W8(r, 8)
+        : "memory");
+}
+// named barrier over `threads` threads (a multiple of 32) of the CTA; id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // math
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {

@@ -18,7 +18,9 @@ multi-device code at all; both modes are built on the single-GPU kernel behind t
    instead of across tiles.
    Causal work is balanced with the zig-zag layout: the sequence is cut into 2P chunks and rank r owns chunks
    r and 2P-1-r, so every rank does the same amount of unmasked work at every step and fully masked block pairs
-   are never launched.
+   are never launched.  Every ring step is ONE kernel launch into the rank's single fp32 accumulator
+   (fa_fwd_carry_window: a step in which only the late local chunk sees the arriving keys addresses the accumulator
+   rows of that chunk), P launches per pass plus one cast.
 
 The ring driver takes the local "attend and fold into the carry" operator as an argument: on GPUs it defaults to
 the CUDA path (fa_b200.attention_forward_carry); the CPU tests (gloo, world_size 2) pass a CPU stand-in to check
@@ -62,22 +64,26 @@ def zigzag_merge(parts, world: int, dim: int = 2):
 
 
 def ring_schedule(world: int, rank: int, causal: bool):
-    """The list of local attention calls of one rank, per ring step.  Each entry is
-    (step, src_rank, q_part, kv_part, causal_flag) with parts in {'a','b','ab'} ('a'/'b' = first / second local
-    chunk, 'ab' = both).  Fully masked block pairs do not appear."""
+    """The local attention call of one rank at every ring step: a list of (step, src_rank, q_part, kv_part, causal_flag)
+    with exactly ONE entry per step.  Parts: 'ab' = all local rows, 'a' / 'b' = first / second local chunk.
+      step 0            ('ab', 'ab', causal)  the rank's own block: in the zig-zag layout chunk a precedes chunk b in the
+                                              global order too, so the local [a ; b] sequence against itself under the
+                                              ordinary causal mask is exactly the two diagonal blocks plus (b, a)
+      sender < rank     ('ab', 'a',  full)    only the sender's early chunk is visible — to both local chunks
+      sender > rank     ('b',  'ab', full)    only the local late chunk sees the sender — both of its chunks
+    Every entry is n^2 / 2 score elements (n = local rows), so all ranks do equal work at every step, and block pairs
+    that are fully masked never reach the GPU (inside the step-0 call the kernel skips masked tiles)."""
     out = []
     for s in range(world):
         src = (rank - s) % world
         if not causal:
             out.append((s, src, "ab", "ab", False))
         elif s == 0:
-            out.append((s, src, "a", "a", True))     # diagonal block of the early chunk
-            out.append((s, src, "b", "ab", True))    # late chunk: all of Ka, causal inside Kb (bottom-right aligned)
+            out.append((s, src, "ab", "ab", True))
         elif src < rank:
-            out.append((s, src, "a", "a", False))    # only the sender's early chunk is visible, to both local chunks
-            out.append((s, src, "b", "a", False))
+            out.append((s, src, "ab", "a", False))
         else:
-            out.append((s, src, "b", "ab", False))   # only the local late chunk sees the sender's (both) chunks
+            out.append((s, src, "b", "ab", False))
     return out
 
 
@@ -85,8 +91,8 @@ def _default_ops():
     import torch
     import fa_b200
 
-    def step(q, k, v, causal, acc_o, acc_lse):
-        fa_b200.attention_forward_carry(q, k, v, acc_o, acc_lse, causal=causal)
+    def step(q, k, v, causal, acc_o, acc_lse, row_offset):
+        fa_b200.attention_forward_carry(q, k, v, acc_o, acc_lse, causal=causal, row_offset=row_offset)
 
     def finish(acc, like):
         return fa_b200.cast_out(acc, torch.empty(acc.shape, dtype=like.dtype, device=acc.device))
@@ -116,31 +122,46 @@ class _PeerRing:
         return self.hdl.get_buffer(rank, self.kv_shape, self.dtype, i * self.numel)
 
 
-_PEER_RINGS = {}
-_PEER_DISABLED = [False]
+_PEER_RINGS = {}          # key -> _PeerRing, or None when the ranks agreed that this key has no symmetric-memory ring
+_PEER_RING_LIMIT = 8      # symmetric buffers kept alive; the least recently created one is dropped beyond this
 
 
 def _peer_ring(kv_shape, dtype, device, group):
-    """Cached symmetric-memory ring for this shape, or None when symmetric memory is unavailable."""
-    if _PEER_DISABLED[0]:
-        return None
+    """Cached symmetric-memory ring for this (shape, dtype, group), or None when it cannot be had.  The decision is
+    COLLECTIVE: every rank tries, the outcomes are combined with an all-reduce (MIN), and either all ranks use the ring or
+    none does — a rank-local failure (out of memory for a new shape, say) can therefore never leave one rank in the
+    point-to-point protocol while the others wait in a symmetric-memory barrier.  A failure is remembered for its own
+    key only."""
+    import torch
+    import torch.distributed as dist
     key = (tuple(kv_shape), dtype, str(device), id(group))
-    if key not in _PEER_RINGS:
-        try:
-            _PEER_RINGS[key] = _PeerRing(kv_shape, dtype, device, group)
-        except Exception as ex:    # rendezvous is collective: it fails (or works) on every rank alike
-            import warnings
-            warnings.warn(f"symmetric-memory ring unavailable ({ex}); using point-to-point send/recv")
-            _PEER_DISABLED[0] = True
-            return None
-    return _PEER_RINGS[key]
+    if key in _PEER_RINGS:
+        return _PEER_RINGS[key]
+    ring, err = None, None
+    try:
+        ring = _PeerRing(kv_shape, dtype, device, group)
+    except Exception as ex:
+        err = ex
+    ok = torch.tensor([1 if ring is not None else 0], device=device, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        if ring is not None:
+            del ring
+        import warnings
+        warnings.warn(f"symmetric-memory ring unavailable on some rank ({err}); using point-to-point send/recv for this shape")
+        ring = None
+    while len(_PEER_RINGS) >= _PEER_RING_LIMIT:
+        _PEER_RINGS.pop(next(iter(_PEER_RINGS)))
+    _PEER_RINGS[key] = ring
+    return ring
 
 
 def ring_attention(q, k, v, causal: bool = True, group=None, step_fn: Optional[Callable] = None,
                    finish_fn: Optional[Callable] = None, return_lse: bool = False, transport: str = "auto"):
     """Sequence-sharded attention.  q [B,Hq,n,d], k/v [B,Hkv,n,d] are this rank's shard of the sequence
     (zig-zag layout when causal: [chunk r ; chunk 2P-1-r], contiguous otherwise).  Returns this rank's shard of O.
-    One send + one recv of the packed K/V block per step, none on the last step."""
+    One K/V hop and ONE attention launch per step (step_fn(q, k, v, causal, acc_o, acc_lse, row_offset) folds the step
+    into the rank's single fp32 accumulator; q's rows are the accumulator's rows [row_offset, row_offset + len(q)))."""
     import torch
     import torch.distributed as dist
 
@@ -167,20 +188,13 @@ def ring_attention(q, k, v, causal: bool = True, group=None, step_fn: Optional[C
             return t
         return t[..., :half, :] if which == "a" else t[..., half:, :]
 
-    f32 = dict(device=q.device, dtype=torch.float32)
-    if causal:
-        acc = {"a": (torch.zeros(B, Hq, half, d, **f32), torch.full((B, Hq, half), float("-inf"), **f32)),
-               "b": (torch.zeros(B, Hq, n - half, d, **f32), torch.full((B, Hq, n - half), float("-inf"), **f32))}
-        qparts = {"a": part(q, "a").contiguous(), "b": part(q, "b").contiguous()}
-    else:
-        acc = {"ab": (torch.zeros(B, Hq, n, d, **f32), torch.full((B, Hq, n), float("-inf"), **f32))}
-        qparts = {"ab": q}
-
+    acc_o = torch.zeros(B, Hq, n, d, device=q.device, dtype=torch.float32)
+    acc_lse = torch.full((B, Hq, n), float("-inf"), device=q.device, dtype=torch.float32)
     sched = ring_schedule(world, rank, causal)
 
     def compute(s, kv):
         for (_, _, qp, kp, c) in [e for e in sched if e[0] == s]:
-            step_fn(qparts[qp], part(kv[0], kp), part(kv[1], kp), c, acc[qp][0], acc[qp][1])
+            step_fn(part(q, qp), part(kv[0], kp), part(kv[1], kp), c, acc_o, acc_lse, half if qp == "b" else 0)
 
     if ring is not None:
         # ---- "peer": pull the predecessor's block out of its symmetric-memory slot on a side stream ----
@@ -215,7 +229,7 @@ def ring_attention(q, k, v, causal: bool = True, group=None, step_fn: Optional[C
             send_to, recv_from = dist.get_global_rank(group, send_to), dist.get_global_rank(group, recv_from)
         for s in range(world):
             reqs = []
-            if s + 1 < world:   # post the hop for the NEXT step first: it overlaps the attention calls below
+            if s + 1 < world:   # post the hop for the NEXT step first: it overlaps the attention call below
                 ops = [dist.P2POp(dist.isend, kv, send_to, group), dist.P2POp(dist.irecv, nxt, recv_from, group)]
                 reqs = dist.batch_isend_irecv(ops)
             compute(s, kv)
@@ -223,9 +237,5 @@ def ring_attention(q, k, v, causal: bool = True, group=None, step_fn: Optional[C
                 r.wait()
             if s + 1 < world:
                 kv, nxt = nxt, kv
-    if causal:
-        o = torch.cat([finish_fn(acc["a"][0], q), finish_fn(acc["b"][0], q)], dim=2)
-        lse = torch.cat([acc["a"][1], acc["b"][1]], dim=2)
-    else:
-        o, lse = finish_fn(acc["ab"][0], q), acc["ab"][1]
-    return (o, lse) if return_lse else o
+    o = finish_fn(acc_o, q)
+    return (o, acc_lse) if return_lse else o

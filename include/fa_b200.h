@@ -16,8 +16,17 @@
  * All functions return FA_OK (0) or a negative error code; none of them calls exit() or assert()
  * (the reference's caller used CUDA_CHECK -> exit(1), tests/main.cu:12-19, and helpers.hpp:34 asserts).
  * All device work is enqueued on the given stream (NULL = default stream); nothing synchronises unless
- * stated.  Functions are re-entrant; the library keeps no mutable global state except an immutable
- * per-device property cache, a launch counter and a thread-local last-error string.
+ * stated.  Threading: every entry point may be called from any number of host threads, on any device and any
+ * stream, concurrently.  The state the library keeps is listed here in full:
+ *   - per device, behind a mutex: the property cache, and one 4-byte work-item counter per stream that has
+ *     launched the persistent kernel (per thread for cudaStreamPerThread; one per launch recorded into a CUDA
+ *     graph) — two launches that can be in flight together never share a counter, and a launch leaves its
+ *     counter zero, so there is no per-launch memset;
+ *   - per device, behind its own mutex: the three streams and staging buffers of fa_fwd_host (calls on one
+ *     device take turns, calls on different devices run side by side);
+ *   - per host thread: the last-error string and a small cache of TMA descriptors keyed by
+ *     (pointer, dtype, shape, strides);
+ *   - process-wide atomics: the launch counter and the fa_set_sm_reserve value.
  */
 #ifndef FA_B200_H_
 #define FA_B200_H_
@@ -96,6 +105,13 @@ int fa_merge_partial(float* acc_o, float* acc_lse, const void* part_o, const flo
 int fa_fwd_carry(const void* Q, const void* K, const void* V, float* acc_o, float* acc_lse,
                  int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype, float scale, int causal,
                  const long long* qkv_strides, void* stream);
+/* fa_fwd_carry_window: fa_fwd_carry where this call's Nq query rows are rows [acc_row_offset, acc_row_offset + Nq) of a
+ * running pair that holds acc_rows rows per (batch, head) (acc_o fp32 [B,Hq,acc_rows,d], acc_lse fp32 [B,Hq,acc_rows]).
+ * A ring step in which only part of the rank's query rows see the arriving keys (zig-zag causal layout: the late half
+ * only) is then ONE launch into the rank's single accumulator — no per-part accumulators, no second launch. */
+int fa_fwd_carry_window(const void* Q, const void* K, const void* V, float* acc_o, float* acc_lse, int acc_rows, int acc_row_offset,
+                        int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype, float scale, int causal,
+                        const long long* qkv_strides, void* stream);
 /* fa_cast_out: fp32 accumulator -> 16-bit output tensor (n elements, n even). */
 int fa_cast_out(const float* src, void* dst, long long n, int dtype, void* stream);
 

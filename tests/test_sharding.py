@@ -37,11 +37,15 @@ def test_ring_schedule_covers_exactly_the_causal_block_pairs(world):
     for r in range(world):
         own = dict(zip("ab", sharding.zigzag_chunks(world, r)))
         w = 0
-        for (s, src, qp, kp, c) in sharding.ring_schedule(world, r, True):
+        sched = sharding.ring_schedule(world, r, True)
+        assert [e[0] for e in sched] == list(range(world)), "exactly one attention launch per ring step"
+        for (s, src, qp, kp, c) in sched:
             assert src == (r - s) % world
             theirs = dict(zip("ab", sharding.zigzag_chunks(world, src)))
             for qn in qp:
                 for kn in kp:
+                    if c and kn > qn:
+                        continue      # inside a causal call the block above the diagonal is masked: the kernel skips its tiles
                     qc, kc = own[qn], theirs[kn]
                     vis = _visible(qc, kc)
                     assert vis > 0, "a fully masked block pair was scheduled"
@@ -54,15 +58,17 @@ def test_ring_schedule_covers_exactly_the_causal_block_pairs(world):
     assert max(work) == min(work), f"zig-zag must balance causal work: {work}"
 
 
-def _cpu_step(q, k, v, causal, acc_o, acc_lse):
-    """CPU stand-in for fa_fwd_carry: oracle attention over this key range, folded into the running (O, LSE) pair."""
+def _cpu_step(q, k, v, causal, acc_o, acc_lse, row_offset):
+    """CPU stand-in for fa_fwd_carry_window: oracle attention over this key range, folded into rows
+    [row_offset, row_offset + Nq) of the running (O, LSE) pair."""
     o, lse = oracle.attention_fwd(q.numpy(), k.numpy(), v.numpy(), causal=causal, return_lse=True)
     o, lse = torch.from_numpy(o), torch.from_numpy(lse)
-    new = torch.logaddexp(acc_lse, lse)
-    wa = torch.exp(acc_lse - new).nan_to_num(0.0)
+    ao, al = acc_o[:, :, row_offset:row_offset + q.shape[2]], acc_lse[:, :, row_offset:row_offset + q.shape[2]]
+    new = torch.logaddexp(al, lse)
+    wa = torch.exp(al - new).nan_to_num(0.0)
     wb = torch.exp(lse - new).nan_to_num(0.0)
-    acc_o.mul_(wa[..., None]).add_(o * wb[..., None])
-    acc_lse.copy_(new)
+    ao.mul_(wa[..., None]).add_(o * wb[..., None])
+    al.copy_(new)
 
 
 def _worker(rank, world, port, causal, shape, ret):
