@@ -309,6 +309,13 @@ def test_stage_probes_tma_umma_tmem():
     assert r.returncode == 0 and "PROBE PASSED" in r.stdout
 
 
+def test_stage_probe_softmax_step():
+    # one online-softmax step on a known score tile, in the 16-lane TMEM view the kernel uses, against a host restatement
+    # (the slot of the reference's empty tests/test_computers.cu)
+    r = _run(os.path.join(PKG, "tests", "probe_softmax"))
+    assert r.returncode == 0 and "SOFTMAX PROBE PASSED" in r.stdout
+
+
 def test_reference_own_test_runs_against_our_headers():
     # the reference's tests/main.cu, unmodified, compiled against our kernels/ (oracle/_ref/ref_test_dropin)
     path = os.path.join(ROOT, "oracle", "_ref", "ref_test_dropin")
