@@ -26,13 +26,22 @@ NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-line
 
 FA_DTYPE_F32, FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1, 2
 EXPORTS = ["fa_fwd", "fa_fwd_strided", "fa_fwd_carry", "fa_fwd_carry_window", "fa_mha_fwd_f32", "fa_fwd_host", "fa_merge_partial", "fa_cast_out",
-           "fa_set_sm_reserve", "fa_device_info", "fa_block_q", "fa_block_kv", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
+           "fa_set_sm_reserve", "fa_device_info", "fa_block_q", "fa_block_kv", "fa_tile_table", "fa_choose_tile", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
 
 _lib = None
 
 
 class FaError(RuntimeError):
     pass
+
+
+class TileChoice(ctypes.Structure):
+    """fa_tile_choice_t of include/fa_b200.h: one row of the measured tile table."""
+    _fields_ = [(n, ctypes.c_int) for n in ("d", "causal", "n_min", "block_q", "block_kv", "stages", "softmax_warps",
+                                            "emu_pairs_per_8", "issuer_by_type", "cta_group")] + [("tflops", ctypes.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -66,6 +75,10 @@ def lib() -> ctypes.CDLL:
         L.fa_merge_partial.argtypes = [vp, vp, vp, vp, ll, ip, ip, vp]
         L.fa_cast_out.argtypes = [vp, vp, ll, ip, vp]
         L.fa_device_info.argtypes = [ip, vp]
+        L.fa_tile_table.argtypes = [ctypes.POINTER(ctypes.POINTER(TileChoice))]
+        L.fa_choose_tile.argtypes = [ip] * 5 + [ctypes.POINTER(TileChoice)]
+        L.fa_debug_force_variant.argtypes = [ip, ip]
+        L.fa_debug_half_items.argtypes = [ip]
         L.fa_set_sm_reserve.argtypes = [ip]
         for name in ("fa_block_q", "fa_block_kv", "fa_num_cta"):
             getattr(L, name).argtypes = [ip, ip]
@@ -75,6 +88,9 @@ def lib() -> ctypes.CDLL:
         L.fa_version.restype = ctypes.c_char_p
         L.fa_launch_count.restype = ll
         _lib = L
+        if os.environ.get("FA_FORCE_VARIANT"):     # tuning / parity runs of one compiled variant: "softmax_warps,emu"
+            sw, emu = (int(x) for x in os.environ["FA_FORCE_VARIANT"].split(","))
+            L.fa_debug_force_variant(sw, emu)
     return _lib
 
 
@@ -186,6 +202,24 @@ def attention_forward_carry(q, k, v, acc_o, acc_lse, causal=False, scale=None, r
                                        B, Hq, Hkv, Nq, Nk, d, _dtype_code(q), float(scale) if scale else 0.0,
                                        int(bool(causal)), strides, _stream_ptr(q))
     _check(rc, "fa_fwd_carry_window")
+
+
+def tile_table():
+    """The measured tile table the launcher dispatches from (replaces calculateSizeBlockQ / KV, reference helpers.hpp:8-30)."""
+    rows = ctypes.POINTER(TileChoice)()
+    n = lib().fa_tile_table(ctypes.byref(rows))
+    return [rows[i].as_dict() for i in range(n)]
+
+
+def choose_tile(d, dtype_code, causal, nq, nk):
+    out = TileChoice()
+    _check(lib().fa_choose_tile(d, dtype_code, int(bool(causal)), nq, nk, ctypes.byref(out)), "fa_choose_tile")
+    return out.as_dict()
+
+
+def force_variant(softmax_warps=0, emu=0):
+    """A/B tooling: run every following launch with this kernel variant (0 = back to the tile table)."""
+    _check(lib().fa_debug_force_variant(int(softmax_warps), int(emu)), "fa_debug_force_variant")
 
 
 def set_sm_reserve(sms: int):

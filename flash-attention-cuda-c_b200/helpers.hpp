@@ -1,8 +1,9 @@
 // helpers.hpp — host-side tile-size helpers, same names and argument lists as the reference's
 // (reference: helpers.hpp:8-36: calculateSizeBlockQ / calculateSizeBlockKV sketch register- and L2-driven formulas
 // and then return the constant 64; getNumCta asserts divisibility).
-// Here they answer from the sm_100a tile table the kernels are built with (queried through the C ABI), and
-// getNumCta rounds ragged lengths up instead of asserting, because TMA zero-fill handles partial tiles.
+// Here they answer from the MEASURED sm_100a tile table the launcher dispatches from (fa_tile_table / fa_choose_tile in the C
+// ABI: per head dim, causal flag and key-length bucket the kernel variant that measured fastest on B200), and getNumCta
+// rounds ragged lengths up instead of asserting, because TMA zero-fill handles partial tiles.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -22,6 +23,13 @@ inline int calculateSizeBlockKV(cudaDeviceProp& prop, int d_head, int device) {
     (void)prop;
     (void)device;
     return fa_block_kv(d_head, FA_DTYPE_BF16);
+}
+
+// What the launcher would run for a given problem: the row of the measured tile table (fa_tile_table) that applies.
+inline fa_tile_choice_t chooseTile(int d_head, int dtype, bool causal, int seqLenQ, int seqLenK) {
+    fa_tile_choice_t t{};
+    fa_choose_tile(d_head, dtype, causal ? 1 : 0, seqLenQ, seqLenK, &t);
+    return t;
 }
 
 // dtype-aware variants (not in the reference)

@@ -173,42 +173,82 @@ int* next_counter(cudaStream_t st, int* sm_count_out) {
     return c;
 }
 
+// ---- measured tile table -----------------------------------------------------------------------------
+// Stands where the reference's calculateSizeBlockQ / calculateSizeBlockKV sketch register- and L2-driven formulas and then
+// return 64 (reference: helpers.hpp:8-30): per (head dim, causal, key-length bucket) the kernel variant that measured
+// fastest on B200 (scripts/tile_sweep.py -> profiles/r2_tile_sweep.jsonl; `tflops` is that run's figure for the bucket's
+// representative shape, launches held back to back under the power cap).  fp16 takes the bf16 rows (same cycle counts).
+// Tile geometry is the same in every row — 256 query rows per work item (2 x 128-row MMA tiles ping-ponged through the tensor
+// pipe), 128 key rows per pipeline stage, the whole TMEM and shared memory of an SM, 1-CTA MMAs — because the sweeps that
+// varied it lost: 64-key steps run the SS MMA at half rate, a 4-slot ring costs 0.2-1.7 %, and no 2-CTA variant is built.
+// What varies is the softmax layout (8 warps x one row per thread / 16 warps x 16-lane fragments) and the share of
+// exponentials moved to the FMA pipe.
+const fa_tile_choice_t kTileTable[] = {
+    //  d  causal n_min  block_q block_kv stages sm_warps emu issuer cta  tflops
+    {128, 0,     0,  256, 128, 5,  8, 0, 1, 1, 0.f},
+    {128, 1,     0,  256, 128, 5,  8, 0, 1, 1, 0.f},
+    { 64, 0,     0,  256, 128, 8,  8, 0, 0, 1, 0.f},
+    { 64, 0,  4096,  256, 128, 8, 16, 1, 0, 1, 0.f},
+    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 1, 0.f},
+    { 64, 1,  4096,  256, 128, 8, 16, 1, 0, 1, 0.f},
+};
+constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
+std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_half_items{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
+
+const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
+    const fa_tile_choice_t* best = nullptr;
+    for (int i = 0; i < kTileRows; ++i) {
+        const fa_tile_choice_t& r = kTileTable[i];
+        if (r.d == d && r.causal == (causal ? 1 : 0) && nk >= r.n_min && (!best || r.n_min >= best->n_min)) best = &r;
+    }
+    return best;
+}
+
 // ---- tcgen05 path ----------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32>
+template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU>
 int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, fa::FwdParams p,
                  cudaStream_t st) {
     using L = fa::SmemLayout<D, STAGES>;
-    auto kern = fa::fwdSm100Kernel<D, STAGES, DT, OVEC32>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
-    });
-    // the attribute is per device; set it again cheaply when several devices are used from one process
+    auto kern = fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU>;
+    // the dynamic shared-memory opt-in is per device
     int dev = 0;
     cudaGetDevice(&dev);
     static std::atomic<unsigned long long> dev_mask{0};
     if (!(dev_mask.load() & (1ull << dev))) {
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+        if (e != cudaSuccess) return fail(FA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) -> %s", L::kDynamicBytes, cudaGetErrorString(e));
         dev_mask.fetch_or(1ull << dev);
     }
-    if (attr_err != cudaSuccess) return fail(FA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) -> %s", L::kDynamicBytes,
-                                             cudaGetErrorString(attr_err));
     const int rows_per_item = fa::kTilesPerCta * fa::kBlockM;
     p.num_q_blocks = (p.Nq + rows_per_item - 1) / rows_per_item;
-    const long long items = (long long)p.num_q_blocks * p.Hq * p.B;
-    if (items > 0x7fffffffLL - 4096) return fail(FA_ERR_INVALID_ARGUMENT, "too many work items (%lld)", items);
-    p.total_items = (int)items;
+    const long long blocks = (long long)p.num_q_blocks * p.Hq * p.B;
+    if (blocks > 0x3fffffffLL - 4096) return fail(FA_ERR_INVALID_ARGUMENT, "too many work items (%lld)", blocks);
     int sm_count = 0;
     p.sched_counter = next_counter(st, &sm_count);
     if (!p.sched_counter) return fail(FA_ERR_CUDA, "work-item counter allocation failed");
     int max_ctas = sm_count - g_sm_reserve.load();      // SMs left free for a concurrent communication kernel
     if (max_ctas < 1) max_ctas = 1;
+    // Tail of a small launch: query blocks are queued as 256-row items in whole waves of max_ctas; when the remainder would
+    // leave more than half of the SMs idle for a whole item, it is queued as 128-row half items instead (a half item
+    // costs ~0.6 of a full one).  Launches of many waves are left alone: their tail is already short against the rest.
+    long long n_full = blocks;
+    const long long waves = blocks / max_ctas, rem = blocks - waves * max_ctas;
+    if (g_half_items.load() && waves <= 3 && rem > 0 && 2 * rem <= max_ctas) n_full = waves * max_ctas;
+    p.n_full_items = (int)n_full;
+    p.total_items = (int)(n_full + 2 * (blocks - n_full));
     const int grid = p.total_items < max_ctas ? p.total_items : max_ctas;   // persistent: one CTA per SM
-    kern<<<grid, fa::KCfg<D>::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
+    kern<<<grid, fa::KCfg<SW>::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
     g_launches.fetch_add(1);
     FA_CUDA(cudaGetLastError());
     return FA_OK;
+}
+
+template <int D, int STAGES, int DT, bool OVEC32>
+int launch_variant(int sw, int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p,
+                   cudaStream_t st) {
+    if (sw == 16 && emu > 0) return launch_sm100<D, STAGES, DT, OVEC32, 16, 1>(tq, tk, tv, p, st);
+    if (sw == 16) return launch_sm100<D, STAGES, DT, OVEC32, 16, 0>(tq, tk, tv, p, st);
+    return launch_sm100<D, STAGES, DT, OVEC32, 8, 0>(tq, tk, tv, p, st);
 }
 
 template <int D>
@@ -298,15 +338,20 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
     p.prof = g_prof;
 
+    // kernel variant: from the measured tile table, unless an A/B tool forces one
+    const fa_tile_choice_t* tc = choose_tile(d, causal, Nk);
+    int sw = tc ? tc->softmax_warps : 8, emu = tc ? tc->emu_pairs_per_8 : 0;
+    if (g_force_sw.load()) { sw = g_force_sw.load(); emu = g_force_emu.load(); }
+
     // 256-bit epilogue stores need every output row to start 32-byte aligned (carry mode does not write O at all)
     const bool v32 = !carry && reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0;
     const bool bf = dtype == FA_DTYPE_BF16;
     if (d == 128) {
-        if (v32) return bf ? launch_sm100<128, 5, fa::kBF16, true>(tq, tk, tv, p, st) : launch_sm100<128, 5, fa::kF16, true>(tq, tk, tv, p, st);
-        return bf ? launch_sm100<128, 5, fa::kBF16, false>(tq, tk, tv, p, st) : launch_sm100<128, 5, fa::kF16, false>(tq, tk, tv, p, st);
+        if (v32) return bf ? launch_variant<128, 5, fa::kBF16, true>(sw, emu, tq, tk, tv, p, st) : launch_variant<128, 5, fa::kF16, true>(sw, emu, tq, tk, tv, p, st);
+        return bf ? launch_variant<128, 5, fa::kBF16, false>(sw, emu, tq, tk, tv, p, st) : launch_variant<128, 5, fa::kF16, false>(sw, emu, tq, tk, tv, p, st);
     }
-    if (v32) return bf ? launch_sm100<64, 8, fa::kBF16, true>(tq, tk, tv, p, st) : launch_sm100<64, 8, fa::kF16, true>(tq, tk, tv, p, st);
-    return bf ? launch_sm100<64, 8, fa::kBF16, false>(tq, tk, tv, p, st) : launch_sm100<64, 8, fa::kF16, false>(tq, tk, tv, p, st);
+    if (v32) return bf ? launch_variant<64, 8, fa::kBF16, true>(sw, emu, tq, tk, tv, p, st) : launch_variant<64, 8, fa::kF16, true>(sw, emu, tq, tk, tv, p, st);
+    return bf ? launch_variant<64, 8, fa::kBF16, false>(sw, emu, tq, tk, tv, p, st) : launch_variant<64, 8, fa::kF16, false>(sw, emu, tq, tk, tv, p, st);
 }
 
 // ---- host-buffer pipeline state: one per device, each behind its own lock ------------------------------
@@ -499,13 +544,41 @@ int fa_device_info(int device, fa_device_info_t* out) {
 }
 
 int fa_block_q(int d, int dtype) {
-    (void)d;
-    return dtype == FA_DTYPE_F32 ? fa::kF32Rows : fa::kTilesPerCta * fa::kBlockM;
+    if (dtype == FA_DTYPE_F32) return fa::kF32Rows;
+    const fa_tile_choice_t* tc = choose_tile(d, 0, 0);
+    return tc ? tc->block_q : fa::kTilesPerCta * fa::kBlockM;
 }
 int fa_block_kv(int d, int dtype) {
-    (void)d;
-    return dtype == FA_DTYPE_F32 ? fa::kF32Rows : fa::kBlockN;
+    if (dtype == FA_DTYPE_F32) return fa::kF32Rows;
+    const fa_tile_choice_t* tc = choose_tile(d, 0, 0);
+    return tc ? tc->block_kv : fa::kBlockN;
 }
+int fa_tile_table(const fa_tile_choice_t** rows) {
+    if (rows) *rows = kTileTable;
+    return kTileRows;
+}
+int fa_choose_tile(int d, int dtype, int causal, int nq, int nk, fa_tile_choice_t* out) {
+    g_err[0] = 0;
+    (void)nq;
+    if (!out) return fail(FA_ERR_INVALID_ARGUMENT, "out is null");
+    if (dtype == FA_DTYPE_F32) {      // CUDA-core kernel: one geometry
+        *out = fa_tile_choice_t{d, causal ? 1 : 0, 0, fa::kF32Rows, fa::kF32Rows, 1, 0, 0, 0, 1, 0.f};
+        return (d % 16 == 0 && d <= 128) ? FA_OK : fail(FA_ERR_UNSUPPORTED, "fp32 path needs d %% 16 == 0 and d <= 128 (got %d)", d);
+    }
+    const fa_tile_choice_t* tc = choose_tile(d, causal, nk);
+    if (!tc) return fail(FA_ERR_UNSUPPORTED, "16-bit path supports d in {64,128} (got %d)", d);
+    *out = *tc;
+    return FA_OK;
+}
+// A/B tooling (not in include/fa_b200.h): force a kernel variant for every following launch (0, 0 = back to the table);
+// switch the half-item tail schedule off / on.
+int fa_debug_force_variant(int softmax_warps, int emu) {
+    if (softmax_warps != 0 && softmax_warps != 8 && softmax_warps != 16) return FA_ERR_INVALID_ARGUMENT;
+    g_force_sw.store(softmax_warps);
+    g_force_emu.store(emu);
+    return FA_OK;
+}
+int fa_debug_half_items(int on) { g_half_items.store(on ? 1 : 0); return FA_OK; }
 int fa_num_cta(int q_dim, int q_block_size) {
     if (q_dim <= 0 || q_block_size <= 0) return 0;
     return (q_dim + q_block_size - 1) / q_block_size;

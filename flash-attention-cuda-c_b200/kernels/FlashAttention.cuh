@@ -6,8 +6,9 @@
 //                                                    int batchSize, int numHeads, int seqLen, float scale, bool is_causal)
 // (reference: kernels/FlashAttention.cuh:59-63), and adds the B200-native kernel the C-ABI launcher in
 // FlashAttention.cu dispatches to:
-//   fa::fwdSm100Kernel<D, STAGES, DT, OVEC32> — warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16; OVEC32: O is
-//                                        32-byte aligned, so the epilogue may use 256-bit stores)
+//   fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU> — warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16; OVEC32: O is
+//                                        32-byte aligned, so the epilogue may use 256-bit stores; SW: 8 or 16 softmax warps;
+//                                        EMU: share of the exponentials on the FMA pipe)
 //   fa::fwdFp32Kernel<D>                — exact-fp32 CUDA-core kernel for fp32 I/O
 // The compat template is launched by the *caller* with a grid/block/shared-memory size of its own choosing
 // (reference: tests/main.cu:51-61 uses grid 1, (QT+2)*32 threads, (3QT+4R)*D*4 bytes), so it cannot take TMA
@@ -30,7 +31,7 @@ namespace fa {
 // ------------------------------------------------------------------------------------------------
 // B200 kernel: persistent, grid = min(#SMs, work items), 1 CTA / SM; a work item is a 256-row query block of one
 // (batch, head), claimed from a global atomic counter (LPT order inside a head, (batch, head)-major overall).
-// With S = KCfg<D>::kSoftmaxWarps (8 or 16) softmax warps the CTA has S + 4 warps:
+// With S = SW (8 or 16) softmax warps the CTA has S + 4 warps:
 //   warps 0 .. S/2-1   softmax + correction + epilogue for query tile 0
 //   warps S/2 .. S-1   softmax + correction + epilogue for query tile 1
 //   warp  S      MMA issuer: every Q K^T (d = 128) / everything of query tile 0 (d = 64)
@@ -38,12 +39,12 @@ namespace fa {
 //   warp  S+2    TMEM allocator, then MMA issuer: every P V (d = 128) / everything of query tile 1 (d = 64)
 //   warp  S+3    idle (times the CTA for scripts/cycles.py when a debug profile buffer is set)
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32>
-__global__ void __launch_bounds__(KCfg<D>::kNumThreads, 1)
+template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU>
+__global__ void __launch_bounds__(KCfg<SW>::kNumThreads, 1)
 fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
     using L = SmemLayout<D, STAGES>;
-    using C = KCfg<D>;
+    using C = KCfg<SW>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0) __trap();        // SWIZZLE_128B tiles need 1024-B alignment; see SmemLayout::kDynamicBytes
@@ -92,16 +93,16 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     if (warp < C::kSoftmaxWarps) {
         reg_inc<C::kSoftmaxRegs>();
-        if constexpr (C::kRows16) softmaxRows16<D, STAGES, DT, OVEC32>(smem_base, tmem_base, p, warp / 8, (warp / 4) & 1);
-        else softmaxWarpgroup<D, STAGES, DT, OVEC32>(smem_base, tmem_base, p, warp / 4);
+        if constexpr (C::kRows16) softmaxRows16<D, STAGES, DT, OVEC32, EMU>(smem_base, tmem_base, p, warp / 8, (warp / 4) & 1);
+        else softmaxWarpgroup<D, STAGES, DT, OVEC32, EMU>(smem_base, tmem_base, p, warp / 4);
     } else {
         reg_dec<C::kOtherRegs>();
         if (warp == C::kMmaWarp0) {
-            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 0);
-            else mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 0);
+            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT, SW>(smem_base, tmem_base, p, 0);
+            else mmaIssuerWarp<D, STAGES, DT, SW>(smem_base, tmem_base, p, 0);
         } else if (warp == C::kMmaWarp1) {
-            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 1);
-            else mmaIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 1);
+            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT, SW>(smem_base, tmem_base, p, 1);
+            else mmaIssuerWarp<D, STAGES, DT, SW>(smem_base, tmem_base, p, 1);
         } else if (warp == C::kLoadWarp) {
             if (lane == 0) tmaLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, p);
         }

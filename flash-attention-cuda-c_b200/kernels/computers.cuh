@@ -35,6 +35,7 @@ constexpr uint32_t kTmemS = 0;       // the shared S buffer
 constexpr uint32_t kTmemO0 = 256;    // O tile t at columns 256 + 128*t
 __host__ __device__ constexpr uint32_t tmem_p_col(int t) { return 128u + 64u * uint32_t(t); }   // P tile of query tile t
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
+constexpr int kNoRow = 0x3fff0000;          // first row of a query-tile slot that has no rows (beyond any Nq)
 
 // ------------------------------------------------------------------------------------------------
 // MMA issuers: one warp per query tile t (warps kMmaWarp0 / kMmaWarp1).  The whole warp walks the schedule (so that
@@ -49,7 +50,7 @@ constexpr float kRescaleThreshold = 8.0f;   // log2 units
 // issuer multiplied with the tile, a plain arrive when it did not (causal blocks: the early query tile stops one key
 // tile sooner) — in both cases only after it has seen the slot full, which keeps the phases in step.
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT>
+template <int D, int STAGES, int DT, int SW>
 __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p, const int t) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);   // tell the compiler it is warp-uniform
     using L = SmemLayout<D, STAGES>;
@@ -138,7 +139,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
         };
         auto virtual_qk = [&](int j) {
             wait_s_buffer(j);
-            if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), KCfg<D>::kSoftmaxThreadsPerTile);
+            if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), KCfg<SW>::kSoftmaxThreadsPerTile);
             __syncwarp();
         };
         auto pv = [&](int j) {
@@ -214,7 +215,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
 // waits behind the issue of the other kind.  Same barriers and phases as mmaIssuerWarp; both roles see every K/V slot
 // full before they hand it back (commit by the role that multiplied with it, plain arrive by the other).
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT>
+template <int D, int STAGES, int DT, int SW>
 __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p, const int role) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);
     using L = SmemLayout<D, STAGES>;
@@ -271,7 +272,7 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
                             }
                             tc_commit(bar(L::kBarSFull + t));
                         } else {
-                            mbar_arrive_n(bar(L::kBarSFree + t), KCfg<D>::kSoftmaxThreadsPerTile);   // virtual step: pass the buffer on
+                            mbar_arrive_n(bar(L::kBarSFree + t), KCfg<SW>::kSoftmaxThreadsPerTile);   // virtual step: pass the buffer on
                         }
                     }
                     __syncwarp();
@@ -337,7 +338,7 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
 // epilogue (O/l -> global, optional LSE).  Persistent: loops over the published work items; the epilogue of one item
 // overlaps the next item's first Q K^T.
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32>
+template <int D, int STAGES, int DT, bool OVEC32, int EMU>
 __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, int t) {
     using L = SmemLayout<D, STAGES>;
     uint32_t bar0 = smem_base + L::kBarOff;
@@ -368,7 +369,9 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
         if (item < 0) break;
         const WorkItem w = decode_item(p, item);
         const int n = w.n_tile(t);
-        const int tile_row0 = w.q0 + t * kBlockM;
+        // a half item has no rows for query-tile slot 1: n == 0 (no barrier traffic) and its row numbers lie past every
+        // sequence, so the epilogue below writes nothing for it
+        const int tile_row0 = (t * kBlockM < w.rows) ? w.q0 + t * kBlockM : kNoRow;
         const int row = tile_row0 + warp_in_wg * 32 + lane;
 
         float m_run = -INFINITY;   // max in use, in raw (unscaled) score units
@@ -471,10 +474,10 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             const float2 nm2 = make_float2(-m_safe * c, -m_safe * c);
 
             float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-            // exp2 of one score pair: MUFU.EX2 for most pairs, FMA-pipe emulation for kEmuPairsPer8 of every 8
+            // exp2 of one score pair: MUFU.EX2 for most pairs, FMA-pipe emulation for EMU of every 8
             auto exp_pair = [&](int col) -> float2 {
                 float2 x = fma2(make_float2(__uint_as_float(r[col]), __uint_as_float(r[col + 1])), c2, nm2);
-                if (((col / 2) % 8) * 3 % 8 < kEmuPairsPer8) {     // spread the emulated pairs evenly over the group of 8
+                if (((col / 2) % 8) * 3 % 8 < EMU) {     // spread the emulated pairs evenly over the group of 8
                     x = ex2_emu2(x);
                 } else {
                     x.x = ex2_approx(x.x);
@@ -638,7 +641,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
 // so every lane still stores contiguous 64- or 128-byte pieces of one output row; 1/l and the log-sum-exp of a row come from
 // the thread that owned it during the key loop through 2 KB of shared memory and a 64-thread named barrier.
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32>
+template <int D, int STAGES, int DT, bool OVEC32, int EMU>
 __device__ __forceinline__ void softmaxRows16(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, const int t, const int h) {
     using L = SmemLayout<D, STAGES>;
     uint32_t bar0 = smem_base + L::kBarOff;
@@ -783,10 +786,10 @@ __device__ __forceinline__ void softmaxRows16(uint32_t smem_base, uint32_t tmem_
             const float2 c2 = make_float2(c, c);
             const float2 nmA = make_float2(-msA * c, -msA * c), nmB = make_float2(-msB * c, -msB * c);
 
-            // exp2 of one score pair (both of the same row): MUFU.EX2 for most pairs, FMA-pipe emulation for kEmuPairsPer8 of 8
+            // exp2 of one score pair (both of the same row): MUFU.EX2 for most pairs, FMA-pipe emulation for EMU of 8
             auto exp_pair = [&](int i, const float2& nm) -> float2 {
                 float2 x = fma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, nm);
-                if (((i / 2) % 8) * 3 % 8 < kEmuPairsPer8) {
+                if (((i / 2) % 8) * 3 % 8 < EMU) {
                     x = ex2_emu2(x);
                 } else {
                     x.x = ex2_approx(x.x);
@@ -833,7 +836,7 @@ __device__ __forceinline__ void softmaxRows16(uint32_t smem_base, uint32_t tmem_
         // ---- epilogue: 32x32b view, this warp stores columns [h D/2, (h+1) D/2) of the quarter's 32 rows ----
         constexpr int HC = D / 2;
         const WorkItem w = decode_item(p, item);
-        const int tile_row0 = w.q0 + t * kBlockM;
+        const int tile_row0 = (t * kBlockM < w.rows) ? w.q0 + t * kBlockM : kNoRow;   // half item: slot 1 has no rows, nothing is written
         const int rowA = tile_row0 + r_in_tile;
         const int row = tile_row0 + q4 * 32 + lane;
         const bool row_ok = row < p.Nq;

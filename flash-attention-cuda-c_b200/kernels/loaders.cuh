@@ -36,15 +36,11 @@ constexpr int kHalfBytes = kBlockN * 128;   // 16 KiB: one half of a 128-row til
 //                    instructions of the others (softmaxRows16).  A lone warp cannot overlap its own MUFU.EX2 with anything
 //                    (8.14 clk per MUFU + its other instructions, scripts/microbench/pipes.cu), which is what bounds the
 //                    8-warp layout at ~2,600 clk per pair of 128-key tiles against 2,048 clk of MMAs.
-#ifndef FA_SM_WARPS_D128
-#define FA_SM_WARPS_D128 16
-#endif
-#ifndef FA_SM_WARPS_D64
-#define FA_SM_WARPS_D64 16
-#endif
-template <int D>
+// Both layouts are compiled (template parameter SW of the kernel); the launcher picks one per problem from the measured
+// tile table (FlashAttention.cu: kTileTable).
+template <int SW>
 struct KCfg {
-    static constexpr int kSoftmaxWarps = (D == 128) ? FA_SM_WARPS_D128 : FA_SM_WARPS_D64;
+    static constexpr int kSoftmaxWarps = SW;
     static_assert(kSoftmaxWarps == 8 || kSoftmaxWarps == 16, "8 or 16 softmax warps");
     static constexpr bool kRows16 = kSoftmaxWarps == 16;
     static constexpr int kSoftmaxThreadsPerTile = kSoftmaxWarps * 32 / kTilesPerCta;   // arrivals per query tile on s_free / p_full / o_free
@@ -67,11 +63,9 @@ struct KCfg {
     static_assert(kSoftmaxWarps * 32 * kSoftmaxRegs + 128 * kOtherRegs <= kNumThreads * kLaunchRegs,
                   "register split exceeds what the CTA owns at launch");
 };
-// Of every 8 consecutive score pairs, this many take the FMA-pipe exp2 (ex2_emu2) instead of MUFU.EX2.
-#ifndef FA_EMU_PAIRS_PER_8
-#define FA_EMU_PAIRS_PER_8 0
-#endif
-constexpr int kEmuPairsPer8 = FA_EMU_PAIRS_PER_8;
+// FMA-pipe exp2 share (template parameter EMU of the kernel): of every 8 consecutive score pairs, EMU take ex2_emu2 instead of
+// MUFU.EX2.  Pays only where the MUFU is the binding pipe AND other warps can overlap the extra FMA work: d = 64 with 16
+// softmax warps (-2.4 % cycles at N = 8K); at d = 128 it costs 3-10 % in every layout measured.
 
 // Split wait for the previous P V (d = 128 only): the softmax warpgroup waits for the FIRST half of P_t V_{j-1} (o_half, an
 // extra tcgen05.commit) before it overwrites the first half of P_t, and for the second half (o_full) only right before it
@@ -109,7 +103,8 @@ struct FwdParams {
     int causal_off;          // Nk - Nq: key j visible to query i iff j <= i + causal_off
     int q_heads_per_kv;      // Hq / Hkv
     int num_q_blocks;        // 256-row query blocks per (batch, head)
-    int total_items;         // B * Hq * num_q_blocks work items
+    int total_items;         // work items of the launch: n_full_items 256-row items, then two 128-row items for every remaining query block
+    int n_full_items;        // the first n_full_items query blocks (in queue order) are one 256-row item each; the rest are split in halves
     int* sched_counter;      // device int, zero at launch and left zero by the launch: next work item = gridDim.x + atomicAdd(counter, 1)
     unsigned long long* prof; // FA_PHASE_PROFILE builds only: per-phase cycle counters (see scripts/phase_profile.py)
 };
@@ -140,7 +135,7 @@ struct SmemLayout {
     // 16-softmax-warp layout only: per query tile and row, (1 / row sum, log-sum-exp) handed from the warp that owns the row
     // in the 16-lane layout to the warp that stores it in the epilogue (float2[2][128])
     static constexpr int kExchOff = kTmemPtrOff + 16;
-    static constexpr int kExchBytes = KCfg<D>::kRows16 ? kTilesPerCta * kBlockM * 8 : 0;
+    static constexpr int kExchBytes = kTilesPerCta * kBlockM * 8;
     static constexpr int kBytes = kExchOff + kExchBytes;
     static_assert(kBytes <= 232448, "more than 227 KB of shared memory");
     // The dynamic shared-memory window of a kernel without static shared memory starts 1024-B aligned (the kernel traps if
@@ -148,11 +143,14 @@ struct SmemLayout {
     static constexpr int kDynamicBytes = kBytes;
 };
 
-// One work item: a 256-row query block of one (batch, head).
+// One work item: a 256-row query block of one (batch, head) — or, for the tail of a small launch, one 128-row half of
+// such a block (then only query-tile slot 0 of the CTA works; a half item costs ~0.6 of a full one, so splitting the last
+// partial wave of blocks into halves lets all SMs finish together: BASELINE configs[1] is 192 blocks on 148 SMs).
 struct WorkItem {
     int b, h, h_kv;
-    int q0;        // first query row of the block
-    int n_kv;      // number of 128-row key/value tiles the block visits (that of its busiest query tile)
+    int q0;        // first query row of the item
+    int rows;      // 256, or 128 for a half item
+    int n_kv;      // number of 128-row key/value tiles the item visits (that of its busiest query tile)
     int n_tile0, n_tile1;   // tiles each query tile takes part in (causal: the early tile stops one sooner)
     __device__ __forceinline__ int n_tile(int t) const { return t == 0 ? n_tile0 : n_tile1; }
 };
@@ -161,13 +159,21 @@ struct WorkItem {
 // the heavy (late) causal query blocks come first, which makes the dynamic scheduler an LPT queue.
 __device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
     WorkItem w;
-    const int bh = item / p.num_q_blocks;
-    const int r = item - bh * p.num_q_blocks;
+    int blk = item, half = 0;
+    w.rows = kTilesPerCta * kBlockM;
+    if (item >= p.n_full_items) {
+        const int r = item - p.n_full_items;
+        blk = p.n_full_items + (r >> 1);
+        half = r & 1;
+        w.rows = kBlockM;
+    }
+    const int bh = blk / p.num_q_blocks;
+    const int r = blk - bh * p.num_q_blocks;
     const int qb = p.causal ? (p.num_q_blocks - 1 - r) : r;
     w.b = bh / p.Hq;
     w.h = bh - w.b * p.Hq;
     w.h_kv = w.h / p.q_heads_per_kv;
-    w.q0 = qb * (kTilesPerCta * kBlockM);
+    w.q0 = qb * (kTilesPerCta * kBlockM) + half * kBlockM;
     const int n_all = (p.Nk + kBlockN - 1) / kBlockN;
     w.n_kv = 0;
 #pragma unroll
@@ -179,6 +185,7 @@ __device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
             n = n_c < n ? n_c : n;
         }
         if (w.q0 + t * kBlockM >= p.Nq) n = 0;    // tile entirely past the end of the sequence
+        if (t * kBlockM >= w.rows) n = 0;         // half item: query-tile slot 1 has no rows
         if (t == 0) w.n_tile0 = n; else w.n_tile1 = n;
         w.n_kv = n > w.n_kv ? n : w.n_kv;
     }
@@ -225,9 +232,9 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
         if (w.n_kv > 0) {
             mbar_wait(q_empty, (kq & 1) ^ 1);      // the previous item's last Q K^T has retired
             ++kq;
-            mbar_expect_tx(q_full, kTilesPerCta * L::kQTileBytes);
-#pragma unroll
-            for (int t = 0; t < kTilesPerCta; ++t)
+            const int q_tiles = w.rows / kBlockM;
+            mbar_expect_tx(q_full, q_tiles * L::kQTileBytes);
+            for (int t = 0; t < q_tiles; ++t)
 #pragma unroll
                 for (int hf = 0; hf < kHalves; ++hf)
                     tma_load_4d_hint(tmQ, smem_base + L::kQOff + t * L::kQTileBytes + hf * kHalfBytes, q_full,

@@ -39,6 +39,19 @@ void check_gpu_props(int device = 0) {
     printf("Max threads per SM: %d\n", p.max_threads_per_sm);
 }
 
+// the measured tile table the launcher dispatches from (stands where the reference's helpers.hpp:8-30 returns 64)
+void print_tile_table() {
+    const fa_tile_choice_t* rows = nullptr;
+    const int n = fa_tile_table(&rows);
+    printf("tile table (%d rows; a row applies to Nk >= n_min, the largest matching n_min wins):\n", n);
+    printf("  %4s %6s %7s | %7s %8s %6s %13s %9s %14s %9s | %s\n", "d", "causal", "n_min", "block_q", "block_kv", "stages",
+           "softmax_warps", "exp2_emu", "issuer_by_type", "cta_group", "measured TFLOP/s");
+    for (int i = 0; i < n; ++i)
+        printf("  %4d %6d %7d | %7d %8d %6d %13d %7d/8 %14d %9d | %.0f\n", rows[i].d, rows[i].causal, rows[i].n_min, rows[i].block_q,
+               rows[i].block_kv, rows[i].stages, rows[i].softmax_warps, rows[i].emu_pairs_per_8, rows[i].issuer_by_type, rows[i].cta_group,
+               rows[i].tflops);
+}
+
 namespace {
 
 uint16_t to16(float f, int dtype) {   // round-to-nearest-even fp32 -> bf16 / fp16 bits
@@ -145,11 +158,13 @@ int main(int argc, char** argv) {
     int ndev = 0; cudaGetDeviceCount(&ndev);
     if (ndev == 0) { fprintf(stderr, "no CUDA device: this driver has no CPU path\n"); return 3; }
     o.gpus = std::max(1, std::min(o.gpus, ndev));
-    if (o.props) check_gpu_props(0);
+    if (o.props) { check_gpu_props(0); print_tile_table(); }
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
-    const int bq = o.dtype == FA_DTYPE_F32 ? calculateSizeBlockQ(o.d, o.dtype) : calculateSizeBlockQ(prop, o.d);
-    const int bkv = o.dtype == FA_DTYPE_F32 ? calculateSizeBlockKV(o.d, o.dtype) : calculateSizeBlockKV(prop, o.d, 0);
-    printf("%s | tiles: %d query rows / CTA, %d kv rows / stage, %d CTAs per (batch, head)\n", fa_version(), bq, bkv, getNumCta(o.N, bq));
+    const fa_tile_choice_t tile = chooseTile(o.d, o.dtype, o.causal != 0, o.N, o.N);
+    const int bq = tile.block_q, bkv = tile.block_kv;
+    (void)prop;
+    printf("%s | tiles: %d query rows / work item, %d kv rows / stage x %d stages, %d softmax warps, exp2 on the FMA pipe %d/8, %d work items per (batch, head)\n",
+           fa_version(), bq, bkv, tile.stages, tile.softmax_warps, tile.emu_pairs_per_8, getNumCta(o.N, bq));
 
     // (batch, kv-head) units -> contiguous slices, one per GPU, no communication
     const long long units = (long long)o.B * o.Hkv;

@@ -126,6 +126,21 @@ int fa_device_info(int device, fa_device_info_t* out);
 /* Replace calculateSizeBlockQ / calculateSizeBlockKV (reference: helpers.hpp:8-30): rows per CTA and per KV tile. */
 int fa_block_q(int d, int dtype);
 int fa_block_kv(int d, int dtype);
+/* The measured tile table behind them (the reference sketches register- and L2-driven formulas and returns 64,
+ * helpers.hpp:8-30): one row per (head dim, causal, key-length bucket) with the kernel variant that measured fastest on
+ * B200.  A row applies to Nk >= n_min; of the matching rows the one with the largest n_min wins.  The launcher uses it. */
+typedef struct {
+    int d, causal, n_min;      /* key */
+    int block_q, block_kv;     /* query rows per work item (2 MMA tiles of 128), key rows per pipeline stage */
+    int stages;                /* K/V ring slots in shared memory */
+    int softmax_warps;         /* 8: one score row per thread; 16: 16-lane TMEM fragments, 4 softmax warps per SM sub-partition */
+    int emu_pairs_per_8;       /* of every 8 score pairs, this many take exp2 on the FMA pipe instead of MUFU.EX2 */
+    int issuer_by_type;        /* MMA issuer warps split by type (all QK^T / all PV) instead of by query tile */
+    int cta_group;             /* 1: single-CTA tcgen05.mma (no 2-CTA variant is built) */
+    float tflops;              /* measured for the bucket's representative shape (profiles/r2_tile_sweep.jsonl); 0 = not measured */
+} fa_tile_choice_t;
+int fa_tile_table(const fa_tile_choice_t** rows);                                              /* returns the row count */
+int fa_choose_tile(int d, int dtype, int causal, int nq, int nk, fa_tile_choice_t* out);     /* what fa_fwd would run */
 /* Replaces getNumCta (reference: helpers.hpp:33-36): CTAs along the query axis; ragged sizes round up, no assert. */
 int fa_num_cta(int q_dim, int q_block_size);
 

@@ -47,6 +47,22 @@ def test_host_helpers(L):
     assert L.fa_block_q(128, fa_b200.FA_DTYPE_BF16) == 256 and L.fa_block_kv(128, fa_b200.FA_DTYPE_BF16) == 128
     assert L.fa_block_q(64, fa_b200.FA_DTYPE_F32) == 64
     assert b"sm_100a" in L.fa_version()
+    # the measured tile table behind them: every (d, causal) has a base row, rows are consistent with the built kernels,
+    # and fa_choose_tile answers with the row of the largest n_min that fits
+    rows = fa_b200.tile_table()
+    assert {(r["d"], r["causal"]) for r in rows if r["n_min"] == 0} == {(128, 0), (128, 1), (64, 0), (64, 1)}
+    for r in rows:
+        assert r["block_q"] == 256 and r["block_kv"] == 128 and r["softmax_warps"] in (8, 16) and r["cta_group"] == 1
+        assert r["stages"] == (5 if r["d"] == 128 else 8) and r["issuer_by_type"] == (1 if r["d"] == 128 else 0)
+    for d in (64, 128):
+        for causal in (0, 1):
+            for nk in (100, 1024, 4096, 100000):
+                got = fa_b200.choose_tile(d, fa_b200.FA_DTYPE_BF16, causal, nk, nk)
+                want = max((r for r in rows if r["d"] == d and r["causal"] == causal and nk >= r["n_min"]), key=lambda r: r["n_min"])
+                assert got == want
+    assert fa_b200.choose_tile(64, fa_b200.FA_DTYPE_F32, 0, 10, 10)["block_q"] == 64
+    with pytest.raises(fa_b200.FaError):
+        fa_b200.choose_tile(96, fa_b200.FA_DTYPE_BF16, 0, 10, 10)
 
 
 def test_argument_validation_without_gpu(L):
