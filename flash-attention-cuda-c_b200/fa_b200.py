@@ -38,7 +38,7 @@ class FaError(RuntimeError):
 class TileChoice(ctypes.Structure):
     """fa_tile_choice_t of include/fa_b200.h: one row of the measured tile table."""
     _fields_ = [(n, ctypes.c_int) for n in ("d", "causal", "n_min", "block_q", "block_kv", "stages", "softmax_warps",
-                                            "emu_pairs_per_8", "issuer_by_type", "cta_group")] + [("tflops", ctypes.c_float)]
+                                            "emu_pairs_per_8", "epilogue_warps", "issuer_by_type", "cta_group")] + [("tflops", ctypes.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -66,31 +66,39 @@ def lib() -> ctypes.CDLL:
                           "(there is no CPU or PyTorch fallback for this path)")
         L = ctypes.CDLL(LIB_PATH)
         vp, ip, fl, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
-        L.fa_fwd.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, vp]
-        L.fa_fwd_strided.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, ctypes.POINTER(ll), vp]
-        L.fa_fwd_carry.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, ctypes.POINTER(ll), vp]
-        L.fa_fwd_carry_window.argtypes = [vp, vp, vp, vp, vp] + [ip] * 9 + [fl, ip, ctypes.POINTER(ll), vp]
-        L.fa_mha_fwd_f32.argtypes = [vp, vp, vp, vp] + [ip] * 4 + [fl, ip, vp]
-        L.fa_fwd_host.argtypes = [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip]
-        L.fa_merge_partial.argtypes = [vp, vp, vp, vp, ll, ip, ip, vp]
-        L.fa_cast_out.argtypes = [vp, vp, ll, ip, vp]
-        L.fa_device_info.argtypes = [ip, vp]
-        L.fa_tile_table.argtypes = [ctypes.POINTER(ctypes.POINTER(TileChoice))]
-        L.fa_choose_tile.argtypes = [ip] * 5 + [ctypes.POINTER(TileChoice)]
-        L.fa_debug_force_variant.argtypes = [ip, ip]
-        L.fa_debug_half_items.argtypes = [ip]
-        L.fa_set_sm_reserve.argtypes = [ip]
-        for name in ("fa_block_q", "fa_block_kv", "fa_num_cta"):
-            getattr(L, name).argtypes = [ip, ip]
+        sigs = {
+            "fa_fwd": [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, vp],
+            "fa_fwd_strided": [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, ctypes.POINTER(ll), vp],
+            "fa_fwd_carry": [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip, ctypes.POINTER(ll), vp],
+            "fa_fwd_carry_window": [vp, vp, vp, vp, vp] + [ip] * 9 + [fl, ip, ctypes.POINTER(ll), vp],
+            "fa_mha_fwd_f32": [vp, vp, vp, vp] + [ip] * 4 + [fl, ip, vp],
+            "fa_fwd_host": [vp, vp, vp, vp, vp] + [ip] * 7 + [fl, ip],
+            "fa_merge_partial": [vp, vp, vp, vp, ll, ip, ip, vp],
+            "fa_cast_out": [vp, vp, ll, ip, vp],
+            "fa_device_info": [ip, vp],
+            "fa_tile_table": [ctypes.POINTER(ctypes.POINTER(TileChoice))],
+            "fa_choose_tile": [ip] * 5 + [ctypes.POINTER(TileChoice)],
+            "fa_debug_force_variant": [ip, ip, ip],
+            "fa_debug_half_items": [ip],
+            "fa_set_sm_reserve": [ip],
+            "fa_block_q": [ip, ip], "fa_block_kv": [ip, ip], "fa_num_cta": [ip, ip],
+        }
+        older = os.environ.get("FA_B200_ALLOW_OLDER_LIB") == "1"     # A/B tools load builds of earlier commits
+        for name, args in sigs.items():
+            if older and not hasattr(L, name):
+                continue
+            getattr(L, name).argtypes = args
         for name in EXPORTS:
+            if older and not hasattr(L, name):
+                continue
             getattr(L, name).restype = ip
         L.fa_last_error.restype = ctypes.c_char_p
         L.fa_version.restype = ctypes.c_char_p
         L.fa_launch_count.restype = ll
         _lib = L
         if os.environ.get("FA_FORCE_VARIANT"):     # tuning / parity runs of one compiled variant: "softmax_warps,emu"
-            sw, emu = (int(x) for x in os.environ["FA_FORCE_VARIANT"].split(","))
-            L.fa_debug_force_variant(sw, emu)
+            sw, emu, epi = (int(x) for x in (os.environ["FA_FORCE_VARIANT"] + ",0").split(",")[:3])
+            L.fa_debug_force_variant(sw, emu, epi)
     return _lib
 
 
@@ -217,9 +225,9 @@ def choose_tile(d, dtype_code, causal, nq, nk):
     return out.as_dict()
 
 
-def force_variant(softmax_warps=0, emu=0):
+def force_variant(softmax_warps=0, emu=0, epi=0):
     """A/B tooling: run every following launch with this kernel variant (0 = back to the tile table)."""
-    _check(lib().fa_debug_force_variant(int(softmax_warps), int(emu)), "fa_debug_force_variant")
+    _check(lib().fa_debug_force_variant(int(softmax_warps), int(emu), int(epi)), "fa_debug_force_variant")
 
 
 def set_sm_reserve(sms: int):

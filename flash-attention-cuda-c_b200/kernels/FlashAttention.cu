@@ -184,16 +184,16 @@ int* next_counter(cudaStream_t st, int* sm_count_out) {
 // What varies is the softmax layout (8 warps x one row per thread / 16 warps x 16-lane fragments) and the share of
 // exponentials moved to the FMA pipe.
 const fa_tile_choice_t kTileTable[] = {
-    //  d  causal n_min  block_q block_kv stages sm_warps emu issuer cta  tflops
-    {128, 0,     0,  256, 128, 5,  8, 0, 1, 1, 0.f},
-    {128, 1,     0,  256, 128, 5,  8, 0, 1, 1, 0.f},
-    { 64, 0,     0,  256, 128, 8,  8, 0, 0, 1, 0.f},
-    { 64, 0,  4096,  256, 128, 8, 16, 1, 0, 1, 0.f},
-    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 1, 0.f},
-    { 64, 1,  4096,  256, 128, 8, 16, 1, 0, 1, 0.f},
+    //  d  causal n_min  block_q block_kv stages sm_warps emu epi issuer cta  tflops
+    {128, 0,     0,  256, 128, 5,  8, 0, 0, 1, 1, 0.f},
+    {128, 1,     0,  256, 128, 5,  8, 0, 0, 1, 1, 0.f},
+    { 64, 0,     0,  256, 128, 8,  8, 0, 0, 0, 1, 0.f},
+    { 64, 0,  2048,  256, 128, 8, 16, 1, 0, 0, 1, 0.f},
+    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 0, 1, 0.f},
+    { 64, 1,  4096,  256, 128, 8, 16, 1, 0, 0, 1, 0.f},
 };
 constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
-std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_half_items{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
+std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_epi{0}, g_half_items{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
 
 const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
     const fa_tile_choice_t* best = nullptr;
@@ -205,11 +205,11 @@ const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
 }
 
 // ---- tcgen05 path ----------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU>
+template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU, int EPI>
 int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, fa::FwdParams p,
                  cudaStream_t st) {
     using L = fa::SmemLayout<D, STAGES>;
-    auto kern = fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU>;
+    auto kern = fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU, EPI>;
     // the dynamic shared-memory opt-in is per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -237,18 +237,20 @@ int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
     p.n_full_items = (int)n_full;
     p.total_items = (int)(n_full + 2 * (blocks - n_full));
     const int grid = p.total_items < max_ctas ? p.total_items : max_ctas;   // persistent: one CTA per SM
-    kern<<<grid, fa::KCfg<SW>::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
+    kern<<<grid, fa::KCfg<SW, EPI>::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
     g_launches.fetch_add(1);
     FA_CUDA(cudaGetLastError());
     return FA_OK;
 }
 
+// compiled variants: (softmax warps, exp2 share, epilogue warpgroup) = (8,0,0) (8,0,1) (16,1,0)
 template <int D, int STAGES, int DT, bool OVEC32>
-int launch_variant(int sw, int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p,
+int launch_variant(int sw, int emu, int epi, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p,
                    cudaStream_t st) {
-    if (sw == 16 && emu > 0) return launch_sm100<D, STAGES, DT, OVEC32, 16, 1>(tq, tk, tv, p, st);
-    if (sw == 16) return launch_sm100<D, STAGES, DT, OVEC32, 16, 0>(tq, tk, tv, p, st);
-    return launch_sm100<D, STAGES, DT, OVEC32, 8, 0>(tq, tk, tv, p, st);
+    (void)emu;
+    if (sw == 16) return launch_sm100<D, STAGES, DT, OVEC32, 16, 1, 0>(tq, tk, tv, p, st);
+    if (epi) return launch_sm100<D, STAGES, DT, OVEC32, 8, 0, 1>(tq, tk, tv, p, st);
+    return launch_sm100<D, STAGES, DT, OVEC32, 8, 0, 0>(tq, tk, tv, p, st);
 }
 
 template <int D>
@@ -340,18 +342,18 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
 
     // kernel variant: from the measured tile table, unless an A/B tool forces one
     const fa_tile_choice_t* tc = choose_tile(d, causal, Nk);
-    int sw = tc ? tc->softmax_warps : 8, emu = tc ? tc->emu_pairs_per_8 : 0;
-    if (g_force_sw.load()) { sw = g_force_sw.load(); emu = g_force_emu.load(); }
+    int sw = tc ? tc->softmax_warps : 8, emu = tc ? tc->emu_pairs_per_8 : 0, epi = tc ? tc->epilogue_warps : 0;
+    if (g_force_sw.load()) { sw = g_force_sw.load(); emu = g_force_emu.load(); epi = g_force_epi.load(); }
 
     // 256-bit epilogue stores need every output row to start 32-byte aligned (carry mode does not write O at all)
     const bool v32 = !carry && reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0;
     const bool bf = dtype == FA_DTYPE_BF16;
     if (d == 128) {
-        if (v32) return bf ? launch_variant<128, 5, fa::kBF16, true>(sw, emu, tq, tk, tv, p, st) : launch_variant<128, 5, fa::kF16, true>(sw, emu, tq, tk, tv, p, st);
-        return bf ? launch_variant<128, 5, fa::kBF16, false>(sw, emu, tq, tk, tv, p, st) : launch_variant<128, 5, fa::kF16, false>(sw, emu, tq, tk, tv, p, st);
+        if (v32) return bf ? launch_variant<128, 5, fa::kBF16, true>(sw, emu, epi, tq, tk, tv, p, st) : launch_variant<128, 5, fa::kF16, true>(sw, emu, epi, tq, tk, tv, p, st);
+        return bf ? launch_variant<128, 5, fa::kBF16, false>(sw, emu, epi, tq, tk, tv, p, st) : launch_variant<128, 5, fa::kF16, false>(sw, emu, epi, tq, tk, tv, p, st);
     }
-    if (v32) return bf ? launch_variant<64, 8, fa::kBF16, true>(sw, emu, tq, tk, tv, p, st) : launch_variant<64, 8, fa::kF16, true>(sw, emu, tq, tk, tv, p, st);
-    return bf ? launch_variant<64, 8, fa::kBF16, false>(sw, emu, tq, tk, tv, p, st) : launch_variant<64, 8, fa::kF16, false>(sw, emu, tq, tk, tv, p, st);
+    if (v32) return bf ? launch_variant<64, 8, fa::kBF16, true>(sw, emu, epi, tq, tk, tv, p, st) : launch_variant<64, 8, fa::kF16, true>(sw, emu, epi, tq, tk, tv, p, st);
+    return bf ? launch_variant<64, 8, fa::kBF16, false>(sw, emu, epi, tq, tk, tv, p, st) : launch_variant<64, 8, fa::kF16, false>(sw, emu, epi, tq, tk, tv, p, st);
 }
 
 // ---- host-buffer pipeline state: one per device, each behind its own lock ------------------------------
@@ -562,7 +564,7 @@ int fa_choose_tile(int d, int dtype, int causal, int nq, int nk, fa_tile_choice_
     (void)nq;
     if (!out) return fail(FA_ERR_INVALID_ARGUMENT, "out is null");
     if (dtype == FA_DTYPE_F32) {      // CUDA-core kernel: one geometry
-        *out = fa_tile_choice_t{d, causal ? 1 : 0, 0, fa::kF32Rows, fa::kF32Rows, 1, 0, 0, 0, 1, 0.f};
+        *out = fa_tile_choice_t{d, causal ? 1 : 0, 0, fa::kF32Rows, fa::kF32Rows, 1, 0, 0, 0, 0, 1, 0.f};
         return (d % 16 == 0 && d <= 128) ? FA_OK : fail(FA_ERR_UNSUPPORTED, "fp32 path needs d %% 16 == 0 and d <= 128 (got %d)", d);
     }
     const fa_tile_choice_t* tc = choose_tile(d, causal, nk);
@@ -572,10 +574,11 @@ int fa_choose_tile(int d, int dtype, int causal, int nq, int nk, fa_tile_choice_
 }
 // A/B tooling (not in include/fa_b200.h): force a kernel variant for every following launch (0, 0 = back to the table);
 // switch the half-item tail schedule off / on.
-int fa_debug_force_variant(int softmax_warps, int emu) {
+int fa_debug_force_variant(int softmax_warps, int emu, int epi) {
     if (softmax_warps != 0 && softmax_warps != 8 && softmax_warps != 16) return FA_ERR_INVALID_ARGUMENT;
     g_force_sw.store(softmax_warps);
     g_force_emu.store(emu);
+    g_force_epi.store(epi);
     return FA_OK;
 }
 int fa_debug_half_items(int on) { g_half_items.store(on ? 1 : 0); return FA_OK; }

@@ -366,8 +366,9 @@ __device__ __forceinline__ uint32_t mask_gt(uint32_t v, int idx, int lim) {
 //   2^x = 2^f with n added to the exponent field (integer add of the magic sum's low bits shifted by 23)
 // Inputs are clamped at -127 (=> 2^-127, flushed to 0), which also makes -inf (masked scores) safe.
 __device__ __forceinline__ float2 ex2_emu2(float2 x) {
-    x.x = fmaxf(x.x, -127.f);
-    x.y = fmaxf(x.y, -127.f);
+    // NaN-propagating clamp (max.NaN): a NaN score must come out as NaN here exactly as it does from MUFU.EX2, not as 2^-127
+    asm("max.NaN.f32 %0, %0, %1;" : "+f"(x.x) : "f"(-127.f));
+    asm("max.NaN.f32 %0, %0, %1;" : "+f"(x.y) : "f"(-127.f));
     uint64_t ux, ut, un, uf, up;
     asm("mov.b64 %0, {%1, %2};" : "=l"(ux) : "f"(x.x), "f"(x.y));
     asm("{\n\t.reg .b64 m;\n\tmov.b64 m, {%2, %2};\n\tadd.rm.ftz.f32x2 %0, %1, m;\n\t}" : "=l"(ut) : "l"(ux), "f"(12582912.f));

@@ -74,7 +74,7 @@ float from16(uint16_t h, int dtype) {
     float f; memcpy(&f, &u, 4); return f;
 }
 
-struct Opt { int B = 8, H = 32, Hkv = 32, N = 8192, d = 128, dtype = FA_DTYPE_BF16, causal = 1, iters = 20, gpus = 1, verify = 1; bool props = false; };
+struct Opt { int B = 8, H = 32, Hkv = 0 /* 0: same as H */, N = 8192, d = 128, dtype = FA_DTYPE_BF16, causal = 1, iters = 20, gpus = 1, verify = 1; bool props = false; };
 
 struct Shard { int dev; long long unit0, units; double ms = 0; double max_err = 0; int rc = 0; std::string err; };
 
@@ -154,6 +154,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--dtype") && i + 1 < argc) { ++i; o.dtype = !strcmp(argv[i], "fp32") ? FA_DTYPE_F32 : !strcmp(argv[i], "fp16") ? FA_DTYPE_F16 : FA_DTYPE_BF16; }
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
     }
+    if (o.Hkv <= 0) o.Hkv = o.H;
     if (o.H % o.Hkv) { fprintf(stderr, "H must be a multiple of Hkv\n"); return 2; }
     int ndev = 0; cudaGetDeviceCount(&ndev);
     if (ndev == 0) { fprintf(stderr, "no CUDA device: this driver has no CPU path\n"); return 3; }

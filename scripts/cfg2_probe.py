@@ -28,9 +28,9 @@ for (B, H, N, d, causal, dt) in shapes:
     q, k, v = (torch.randn(B, H, N, d, device="cuda", generator=g).to(dt) for _ in range(3))
     o = torch.empty_like(q)
     F = 4.0 * B * H * N * N * d * (0.5 if causal else 1.0)
-    for (sw, emu) in ((8, 0), (16, 0), (16, 1)):
+    for (sw, emu, epi) in ((8, 0, 0), (8, 0, 1), (16, 1, 0)):
         for half in (0, 1):
-            fa_b200.force_variant(sw, emu); L.fa_debug_half_items(half)
+            fa_b200.force_variant(sw, emu, epi); L.fa_debug_half_items(half)
             fn = lambda: fa_b200.attention_forward(q, k, v, causal=causal, out=o)
             eager = timeit(fn, 200)
             gr = torch.cuda.CUDAGraph()
@@ -41,7 +41,7 @@ for (B, H, N, d, causal, dt) in shapes:
             for _ in range(5):
                 prof.zero_(); fn(); torch.cuda.synchronize(); cyc.append(int(prof[30].item()))
             L.fa_debug_set_profile_buffer(None)
-            print(json.dumps({"shape": f"B{B}_H{H}_N{N}_d{d}_{'c' if causal else 'nc'}", "softmax_warps": sw, "emu": emu, "half_items": half,
+            print(json.dumps({"shape": f"B{B}_H{H}_N{N}_d{d}_{'c' if causal else 'nc'}", "softmax_warps": sw, "emu": emu, "epilogue_warps": epi, "half_items": half,
                               "eager_us": round(eager * 1e3, 2), "graph_us": round(graph * 1e3, 2), "tflops_graph": round(F / graph / 1e9, 1),
                               "max_cta_cycles": min(cyc)}), flush=True)
-fa_b200.force_variant(0, 0); L.fa_debug_half_items(1)
+fa_b200.force_variant(0, 0, 0); L.fa_debug_half_items(1)
