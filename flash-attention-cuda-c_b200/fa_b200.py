@@ -38,7 +38,7 @@ class FaError(RuntimeError):
 class TileChoice(ctypes.Structure):
     """fa_tile_choice_t of include/fa_b200.h: one row of the measured tile table."""
     _fields_ = [(n, ctypes.c_int) for n in ("d", "causal", "n_min", "block_q", "block_kv", "stages", "softmax_warps",
-                                            "emu_pairs_per_8", "epilogue_warps", "issuer_by_type", "cta_group")] + [("tflops", ctypes.c_float)]
+                                            "emu_pairs_per_8", "staged_epilogue", "issuer_by_type", "cta_group")] + [("tflops", ctypes.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -225,9 +225,9 @@ def choose_tile(d, dtype_code, causal, nq, nk):
     return out.as_dict()
 
 
-def force_variant(softmax_warps=0, emu=0, epi=0):
+def force_variant(softmax_warps=0, emu=0, staged=0):
     """A/B tooling: run every following launch with this kernel variant (0 = back to the tile table)."""
-    _check(lib().fa_debug_force_variant(int(softmax_warps), int(emu), int(epi)), "fa_debug_force_variant")
+    _check(lib().fa_debug_force_variant(int(softmax_warps), int(emu), int(staged)), "fa_debug_force_variant")
 
 
 def set_sm_reserve(sms: int):

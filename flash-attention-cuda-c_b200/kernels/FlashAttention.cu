@@ -176,24 +176,26 @@ int* next_counter(cudaStream_t st, int* sm_count_out) {
 // ---- measured tile table -----------------------------------------------------------------------------
 // Stands where the reference's calculateSizeBlockQ / calculateSizeBlockKV sketch register- and L2-driven formulas and then
 // return 64 (reference: helpers.hpp:8-30): per (head dim, causal, key-length bucket) the kernel variant that measured
-// fastest on B200 (scripts/tile_sweep.py -> profiles/r2_tile_sweep.jsonl; `tflops` is that run's figure for the bucket's
-// representative shape, launches held back to back under the power cap).  fp16 takes the bf16 rows (same cycle counts).
+// fastest on B200 (scripts/tile_sweep.py -> profiles/r2_tile_sweep.jsonl: 28 shapes x the three compiled variants, launches
+// held back to back under the power cap; `tflops` is that run's figure).  fp16 takes the bf16 rows (same cycle counts).
 // Tile geometry is the same in every row — 256 query rows per work item (2 x 128-row MMA tiles ping-ponged through the tensor
 // pipe), 128 key rows per pipeline stage, the whole TMEM and shared memory of an SM, 1-CTA MMAs — because the sweeps that
-// varied it lost: 64-key steps run the SS MMA at half rate, a 4-slot ring costs 0.2-1.7 %, and no 2-CTA variant is built.
-// What varies is the softmax layout (8 warps x one row per thread / 16 warps x 16-lane fragments) and the share of
-// exponentials moved to the FMA pipe.
+// varied it lost: 64-key steps run the SS MMA at half rate, and no 2-CTA variant is built.  What varies is the softmax
+// layout (8 warps x one row per thread / 16 warps x 16-lane fragments), the share of exponentials moved to the FMA pipe,
+// and how O leaves the SM (row-per-lane st.global, or staged through shared memory + TMA stores, which at d = 128 costs
+// the K/V ring its fifth slot).
 const fa_tile_choice_t kTileTable[] = {
-    //  d  causal n_min  block_q block_kv stages sm_warps emu epi issuer cta  tflops
-    {128, 0,     0,  256, 128, 5,  8, 0, 0, 1, 1, 0.f},
-    {128, 1,     0,  256, 128, 5,  8, 0, 0, 1, 1, 0.f},
-    { 64, 0,     0,  256, 128, 8,  8, 0, 0, 0, 1, 0.f},
-    { 64, 0,  2048,  256, 128, 8, 16, 1, 0, 0, 1, 0.f},
-    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 0, 1, 0.f},
-    { 64, 1,  4096,  256, 128, 8, 16, 1, 0, 0, 1, 0.f},
+    //  d  causal n_min  block_q block_kv stages sm_warps emu staged issuer cta  tflops (first bucket of the row: N = n_min, or 512)
+    {128, 0,     0,  256, 128, 4,  8, 0, 1, 1, 1,  931.2f},   // N = 512: +10 % over direct stores, N = 1024: +1.5 %
+    {128, 0,  2048,  256, 128, 5,  8, 0, 0, 1, 1, 1159.2f},   // N >= 2K: the 5th ring slot is worth more than the staged epilogue (2-4 %)
+    {128, 1,     0,  256, 128, 5,  8, 0, 0, 1, 1,  518.3f},   // causal: direct stores at every length (staged: -0.5 .. -8 %)
+    { 64, 0,     0,  256, 128, 8,  8, 0, 1, 0, 1,  645.4f},   // N = 512: +7 %, N = 1024 (BASELINE configs[1]): +4.4 %
+    { 64, 0,  2048,  256, 128, 8, 16, 1, 0, 0, 1,  767.7f},   // MUFU-bound: 16 softmax warps + 1/8 of the exponentials on the FMA pipe, +2 .. +6 %
+    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 0, 1,  354.6f},
+    { 64, 1,  4096,  256, 128, 8, 16, 1, 0, 0, 1,  722.2f},   // +1 % at 4K, +3 % at 8K, +6 .. +8 % from 16K
 };
 constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
-std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_epi{0}, g_half_items{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
+std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_half_items{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
 
 const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
     const fa_tile_choice_t* best = nullptr;
@@ -205,18 +207,19 @@ const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
 }
 
 // ---- tcgen05 path ----------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU, int EPI>
-int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, fa::FwdParams p,
+template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU, int ST>
+int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, fa::FwdParams p,
                  cudaStream_t st) {
     using L = fa::SmemLayout<D, STAGES>;
-    auto kern = fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU, EPI>;
+    auto kern = fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU, ST>;
+    constexpr int kSmem = ST ? L::kBytesStaged : L::kDynamicBytes;
     // the dynamic shared-memory opt-in is per device
     int dev = 0;
     cudaGetDevice(&dev);
     static std::atomic<unsigned long long> dev_mask{0};
     if (!(dev_mask.load() & (1ull << dev))) {
-        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
-        if (e != cudaSuccess) return fail(FA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) -> %s", L::kDynamicBytes, cudaGetErrorString(e));
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return fail(FA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) -> %s", kSmem, cudaGetErrorString(e));
         dev_mask.fetch_or(1ull << dev);
     }
     const int rows_per_item = fa::kTilesPerCta * fa::kBlockM;
@@ -237,20 +240,22 @@ int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
     p.n_full_items = (int)n_full;
     p.total_items = (int)(n_full + 2 * (blocks - n_full));
     const int grid = p.total_items < max_ctas ? p.total_items : max_ctas;   // persistent: one CTA per SM
-    kern<<<grid, fa::KCfg<SW, EPI>::kNumThreads, L::kDynamicBytes, st>>>(tq, tk, tv, p);
+    kern<<<grid, fa::KCfg<SW>::kNumThreads, kSmem, st>>>(tq, tk, tv, to, p);
     g_launches.fetch_add(1);
     FA_CUDA(cudaGetLastError());
     return FA_OK;
 }
 
-// compiled variants: (softmax warps, exp2 share, epilogue warpgroup) = (8,0,0) (8,0,1) (16,1,0)
-template <int D, int STAGES, int DT, bool OVEC32>
-int launch_variant(int sw, int emu, int epi, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::FwdParams& p,
-                   cudaStream_t st) {
+// compiled variants: (softmax warps, exp2 share on the FMA pipe, staged TMA-store epilogue) = (8,0,0) (8,0,1) (16,1,0); the staged
+// epilogue takes its 32 KiB of shared memory from the K/V ring at d = 128 (4 slots instead of 5) and from spare room at d = 64
+template <int D, int DT, bool OVEC32>
+int launch_variant(int sw, int emu, int stg, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                   const fa::FwdParams& p, cudaStream_t st) {
     (void)emu;
-    if (sw == 16) return launch_sm100<D, STAGES, DT, OVEC32, 16, 1, 0>(tq, tk, tv, p, st);
-    if (epi) return launch_sm100<D, STAGES, DT, OVEC32, 8, 0, 1>(tq, tk, tv, p, st);
-    return launch_sm100<D, STAGES, DT, OVEC32, 8, 0, 0>(tq, tk, tv, p, st);
+    constexpr int kStages = D == 128 ? 5 : 8;
+    if (sw == 16) return launch_sm100<D, kStages, DT, OVEC32, 16, 1, 0>(tq, tk, tv, to, p, st);
+    if (stg) return launch_sm100<D, (D == 128 ? 4 : 8), DT, OVEC32, 8, 0, 1>(tq, tk, tv, to, p, st);
+    return launch_sm100<D, kStages, DT, OVEC32, 8, 0, 0>(tq, tk, tv, to, p, st);
 }
 
 template <int D>
@@ -342,18 +347,24 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
 
     // kernel variant: from the measured tile table, unless an A/B tool forces one
     const fa_tile_choice_t* tc = choose_tile(d, causal, Nk);
-    int sw = tc ? tc->softmax_warps : 8, emu = tc ? tc->emu_pairs_per_8 : 0, epi = tc ? tc->epilogue_warps : 0;
-    if (g_force_sw.load()) { sw = g_force_sw.load(); emu = g_force_emu.load(); epi = g_force_epi.load(); }
+    int sw = tc ? tc->softmax_warps : 8, emu = tc ? tc->emu_pairs_per_8 : 0, stg = tc ? tc->staged_epilogue : 0;
+    if (g_force_sw.load()) { sw = g_force_sw.load(); emu = g_force_emu.load(); stg = g_force_stg.load(); }
+    if (carry) stg = 0;      // carry mode folds into an fp32 accumulator in place: there is no 16-bit O to stage
 
-    // 256-bit epilogue stores need every output row to start 32-byte aligned (carry mode does not write O at all)
+    // the staged epilogue writes O with TMA stores (16-byte alignment, checked above); otherwise 256-bit epilogue stores need
+    // every output row to start 32-byte aligned (carry mode does not write O at all)
+    CUtensorMap to = tq;
+    if (stg && sw == 8) {
+        if (int rc = make_tile_map(&to, O, dtype, B, Hq, Nq, d, s[9], s[10], s[11])) return rc;
+    }
     const bool v32 = !carry && reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0;
     const bool bf = dtype == FA_DTYPE_BF16;
     if (d == 128) {
-        if (v32) return bf ? launch_variant<128, 5, fa::kBF16, true>(sw, emu, epi, tq, tk, tv, p, st) : launch_variant<128, 5, fa::kF16, true>(sw, emu, epi, tq, tk, tv, p, st);
-        return bf ? launch_variant<128, 5, fa::kBF16, false>(sw, emu, epi, tq, tk, tv, p, st) : launch_variant<128, 5, fa::kF16, false>(sw, emu, epi, tq, tk, tv, p, st);
+        if (v32) return bf ? launch_variant<128, fa::kBF16, true>(sw, emu, stg, tq, tk, tv, to, p, st) : launch_variant<128, fa::kF16, true>(sw, emu, stg, tq, tk, tv, to, p, st);
+        return bf ? launch_variant<128, fa::kBF16, false>(sw, emu, stg, tq, tk, tv, to, p, st) : launch_variant<128, fa::kF16, false>(sw, emu, stg, tq, tk, tv, to, p, st);
     }
-    if (v32) return bf ? launch_variant<64, 8, fa::kBF16, true>(sw, emu, epi, tq, tk, tv, p, st) : launch_variant<64, 8, fa::kF16, true>(sw, emu, epi, tq, tk, tv, p, st);
-    return bf ? launch_variant<64, 8, fa::kBF16, false>(sw, emu, epi, tq, tk, tv, p, st) : launch_variant<64, 8, fa::kF16, false>(sw, emu, epi, tq, tk, tv, p, st);
+    if (v32) return bf ? launch_variant<64, fa::kBF16, true>(sw, emu, stg, tq, tk, tv, to, p, st) : launch_variant<64, fa::kF16, true>(sw, emu, stg, tq, tk, tv, to, p, st);
+    return bf ? launch_variant<64, fa::kBF16, false>(sw, emu, stg, tq, tk, tv, to, p, st) : launch_variant<64, fa::kF16, false>(sw, emu, stg, tq, tk, tv, to, p, st);
 }
 
 // ---- host-buffer pipeline state: one per device, each behind its own lock ------------------------------
@@ -574,11 +585,11 @@ int fa_choose_tile(int d, int dtype, int causal, int nq, int nk, fa_tile_choice_
 }
 // A/B tooling (not in include/fa_b200.h): force a kernel variant for every following launch (0, 0 = back to the table);
 // switch the half-item tail schedule off / on.
-int fa_debug_force_variant(int softmax_warps, int emu, int epi) {
+int fa_debug_force_variant(int softmax_warps, int emu, int staged) {
     if (softmax_warps != 0 && softmax_warps != 8 && softmax_warps != 16) return FA_ERR_INVALID_ARGUMENT;
     g_force_sw.store(softmax_warps);
     g_force_emu.store(emu);
-    g_force_epi.store(epi);
+    g_force_stg.store(staged);
     return FA_OK;
 }
 int fa_debug_half_items(int on) { g_half_items.store(on ? 1 : 0); return FA_OK; }

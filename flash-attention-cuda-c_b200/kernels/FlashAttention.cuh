@@ -6,9 +6,10 @@
 //                                                    int batchSize, int numHeads, int seqLen, float scale, bool is_causal)
 // (reference: kernels/FlashAttention.cuh:59-63), and adds the B200-native kernel the C-ABI launcher in
 // FlashAttention.cu dispatches to:
-//   fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU> — warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16; OVEC32: O is
+//   fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU, ST> — warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16; OVEC32: O is
 //                                        32-byte aligned, so the epilogue may use 256-bit stores; SW: 8 or 16 softmax warps;
-//                                        EMU: share of the exponentials on the FMA pipe)
+//                                        EMU: share of the exponentials on the FMA pipe; ST: epilogue staged
+//                                        through shared memory and written with TMA stores)
 //   fa::fwdFp32Kernel<D>                — exact-fp32 CUDA-core kernel for fp32 I/O
 // The compat template is launched by the *caller* with a grid/block/shared-memory size of its own choosing
 // (reference: tests/main.cu:51-61 uses grid 1, (QT+2)*32 threads, (3QT+4R)*D*4 bytes), so it cannot take TMA
@@ -38,14 +39,13 @@ namespace fa {
 //   warp  S+1    TMA producer + scheduler (one thread)
 //   warp  S+2    TMEM allocator, then MMA issuer: every P V (d = 128) / everything of query tile 1 (d = 64)
 //   warp  S+3    idle (times the CTA for scripts/cycles.py when a debug profile buffer is set)
-//   warps S+4 .. S+7   (EPI = 1, S = 8 only) epilogue warpgroup: O out of TMEM -> scale -> global, one warp per TMEM lane quarter
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU, int EPI>
-__global__ void __launch_bounds__(KCfg<SW, EPI>::kNumThreads, 1)
+template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU, int ST>
+__global__ void __launch_bounds__(KCfg<SW>::kNumThreads, 1)
 fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const FwdParams p) {
     using L = SmemLayout<D, STAGES>;
-    using C = KCfg<SW, EPI>;
+    using C = KCfg<SW>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0) __trap();        // SWIZZLE_128B tiles need 1024-B alignment; see SmemLayout::kDynamicBytes
@@ -70,17 +70,16 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(bar0 + 8 * (L::kBarOFull + t), 1);
             mbar_init(bar0 + 8 * (L::kBarOFree + t), C::kSoftmaxThreadsPerTile);
             mbar_init(bar0 + 8 * (L::kBarSchedFull + t), 1);
-            mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), C::kItemConsumers);   // both MMA issuers + every softmax (and epilogue) warp
+            mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 2 + C::kSoftmaxWarps);   // both MMA issuers + every softmax warp
             mbar_init(bar0 + 8 * (L::kBarSFree + t), C::kSoftmaxThreadsPerTile);
             mbar_init(bar0 + 8 * (L::kBarOHalf + t), 1);
-            mbar_init(bar0 + 8 * (L::kBarLFull + t), kBlockM);
-            mbar_init(bar0 + 8 * (L::kBarLFree + t), kBlockM);
         }
         fence_mbar_init();
     } else if (warp == C::kLoadWarp && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
+        if (ST != 0) tma_prefetch_desc(&tmO);
     } else if (warp == C::kTmemWarp) {
         tmem_alloc(smem_base + L::kTmemPtrOff, kTmemCols);
         tmem_relinquish();
@@ -92,15 +91,12 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // Cycle counter for A/B work (fa_debug_set_profile_buffer): the otherwise idle last warp times the CTA from here to the
     // final barrier; prof[30] = max over CTAs, prof[31] = sum.  Wall-clock A/B on a power-capped GPU is too noisy.
     long long cta_t0 = 0;
-    if (p.prof != nullptr && threadIdx.x == (C::kSoftmaxWarps + 3) * 32) cta_t0 = clock64();
+    if (p.prof != nullptr && threadIdx.x == C::kNumThreads - 32) cta_t0 = clock64();
 
     if (warp < C::kSoftmaxWarps) {
         reg_inc<C::kSoftmaxRegs>();
         if constexpr (C::kRows16) softmaxRows16<D, STAGES, DT, OVEC32, EMU>(smem_base, tmem_base, p, warp / 8, (warp / 4) & 1);
-        else softmaxWarpgroup<D, STAGES, DT, OVEC32, EMU, EPI>(smem_base, tmem_base, p, warp / 4);
-    } else if (C::kEpiWarps && warp >= C::kEpiWarp0) {
-        reg_dec<C::kEpilogueRegs>();
-        epilogueWarp<D, STAGES, DT, OVEC32>(smem_base, tmem_base, p, warp - C::kEpiWarp0);
+        else softmaxWarpgroup<D, STAGES, DT, OVEC32, EMU, ST>(smem_base, tmem_base, p, warp / 4, &tmO);
     } else {
         reg_dec<C::kOtherRegs>();
         if (warp == C::kMmaWarp0) {
@@ -120,7 +116,7 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
-    if (p.prof != nullptr && threadIdx.x == (C::kSoftmaxWarps + 3) * 32) {
+    if (p.prof != nullptr && threadIdx.x == C::kNumThreads - 32) {
         const unsigned long long dt = (unsigned long long)(clock64() - cta_t0);
         atomicMax(p.prof + 30, dt);
         atomicAdd(p.prof + 31, dt);

@@ -139,7 +139,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
         };
         auto virtual_qk = [&](int j) {
             wait_s_buffer(j);
-            if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), KCfg<SW, 0>::kSoftmaxThreadsPerTile);
+            if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), KCfg<SW>::kSoftmaxThreadsPerTile);
             __syncwarp();
         };
         auto pv = [&](int j) {
@@ -272,7 +272,7 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
                             }
                             tc_commit(bar(L::kBarSFull + t));
                         } else {
-                            mbar_arrive_n(bar(L::kBarSFree + t), KCfg<SW, 0>::kSoftmaxThreadsPerTile);   // virtual step: pass the buffer on
+                            mbar_arrive_n(bar(L::kBarSFree + t), KCfg<SW>::kSoftmaxThreadsPerTile);   // virtual step: pass the buffer on
                         }
                     }
                     __syncwarp();
@@ -338,8 +338,8 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
 // epilogue (O/l -> global, optional LSE).  Persistent: loops over the published work items; the epilogue of one item
 // overlaps the next item's first Q K^T.
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32, int EMU, int EPI>
-__device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, int t) {
+template <int D, int STAGES, int DT, bool OVEC32, int EMU, int ST>
+__device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, int t, const CUtensorMap* tmO) {
     using L = SmemLayout<D, STAGES>;
     uint32_t bar0 = smem_base + L::kBarOff;
     asm volatile("" : "+r"(bar0));     // keep in a register (see below)
@@ -364,7 +364,6 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
 
     FA_PROF_DECL(6);
     int st = 0;      // key tiles this warpgroup has processed so far (barrier phase bookkeeping)
-    int kl = 0;      // EPI: items with work so far (phase bookkeeping of the exchange area)
     for (int k = 0;; ++k) {
         const int item = fetch_item<D, STAGES>(smem_base, k);
         if (item < 0) break;
@@ -535,22 +534,6 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             l_run += (s0.x + s0.y) + (s1.x + s1.y);
         }
 
-        if constexpr (EPI != 0) {
-            // ---- hand the row statistics to the epilogue warpgroup and go straight on to the next item ----
-            if (n > 0) {
-                const uint32_t l_full = bar0 + 8u * (L::kBarLFull + t), l_free = bar0 + 8u * (L::kBarLFree + t);
-                mbar_wait(l_free, (kl & 1) ^ 1);        // the exchange area of the previous item with work has been read
-                ++kl;
-                const float m_fin = (m_run == -INFINITY) ? 0.f : m_run;
-                const float lse_part = (l_run > 0.f) ? (m_fin * p.scale + logf(l_run)) : -INFINITY;
-                const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(smem_base + L::kExchOff + uint32_t(t * kBlockM + warp_in_wg * 32 + lane) * 8u),
-                             "f"(inv_l), "f"(lse_part) : "memory");
-                mbar_arrive(l_full);
-            }
-            st += n;
-            continue;
-        }
         // ---- epilogue ----
         const bool row_ok = row < p.Nq;
         const long long row_lin = ((long long)w.b * p.Hq + w.h) * p.Nq + row;
@@ -561,7 +544,48 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
             uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)w.b * p.o_stride_b + (long long)w.h * p.o_stride_h +
                              (long long)row * p.o_stride_n;
-            if (n > 0) {
+            if (ST != 0 && n > 0) {
+                // Staged epilogue: O / l -> this tile's 16 KiB piece of shared memory (128 rows x 64 columns, the 128B-swizzled
+                // layout of the TMA box) -> one TMA store per 64 columns.  A row-per-lane st.global touches 32 different lines
+                // per instruction (1,024 sector writes per tile, which the LSU takes ~1,000 clk to drain while the warpgroup
+                // could be exponentiating the next item's first score tile); the TMA store writes whole lines and costs the
+                // warps 16 st.shared.v4 per thread.  Rows past Nq are clipped by the tensor map.
+                mbar_wait(o_full, (st + n - 1) & 1);
+                tc_fence_after();
+                const uint32_t stg = smem_base + L::kStageOff + uint32_t(t) * L::kStageTileBytes;
+                const int r_in = warp_in_wg * 32 + lane;
+                const uint32_t srow = stg + uint32_t(r_in) * 128u;
+                const bool leader = (threadIdx.x & 127) == 0;
+#pragma unroll
+                for (int hf = 0; hf < D / kHalfCols; ++hf) {
+                    if (leader) bulk_wait_group_read0();          // the previous store out of this piece has read it
+                    named_bar_sync(1u + uint32_t(t), 128u);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + 64u * hf + 32u * q, o);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {                 // 16-byte chunk 4q + i of the row, XOR-swizzled by row % 8
+                            uint32_t hw[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                hw[e] = pack16<DT>(__uint_as_float(o[8 * i + 2 * e]) * inv_l, __uint_as_float(o[8 * i + 2 * e + 1]) * inv_l);
+                            st_shared_v4(srow + (uint32_t((4 * q + i) ^ (r_in & 7)) << 4), hw[0], hw[1], hw[2], hw[3]);
+                        }
+                    }
+                    if (hf == D / kHalfCols - 1) {                    // O is out of TMEM: the next item's first P V may overwrite it
+                        tc_fence_before();
+                        mbar_arrive(o_free);
+                    }
+                    fence_proxy_async_shared();
+                    named_bar_sync(1u + uint32_t(t), 128u);
+                    if (leader) {
+                        tma_store_4d(tmO, stg, hf * kHalfCols, tile_row0, w.h, w.b);
+                        bulk_commit_group();
+                    }
+                }
+            } else if (n > 0) {
                 mbar_wait(o_full, (st + n - 1) & 1);
                 tc_fence_after();
 #pragma unroll
@@ -641,6 +665,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
         st += n;
     }
     if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 0, 6);
+    if (ST != 0 && (threadIdx.x & 127) == 0) bulk_wait_group0();     // this thread's TMA stores have landed before the CTA exits
     tc_fence_before();
 }
 
@@ -959,112 +984,6 @@ __device__ __forceinline__ void softmaxRows16(uint32_t smem_base, uint32_t tmem_
             mbar_arrive(o_free);
         }
         st += n;
-    }
-    tc_fence_before();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Epilogue warpgroup (KCfg<8, 1>): warp e of four serves TMEM lane quarter e of BOTH query tiles.  Per item and tile it takes
-// (1/l, lse) of its row from the exchange area the softmax warpgroup filled, waits for the item's last P V, reads O out of
-// TMEM 16 columns at a time, scales, packs and stores it (or folds it into the fp32 running pair in carry mode), then
-// hands the O columns back (o_free).  The softmax warpgroups meanwhile are already exponentiating the next item's first
-// score tile: with the epilogue on their own instruction stream an item boundary cost them 2.4 % of all cycles at
-// N = 8K, 8 % at 2K and 13 % at 1K (profiles/r1_phase_profile.md, NOST).  o_full[t] cannot move on to the next item's
-// phase before these warps have seen the current one: the next item's first P_t V waits for their o_free[t].
-// ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32>
-__device__ __forceinline__ void epilogueWarp(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, const int e) {
-    using L = SmemLayout<D, STAGES>;
-    const uint32_t bar0 = smem_base + L::kBarOff;
-    const int lane = threadIdx.x & 31;
-    const uint32_t tO0 = tmem_base + (uint32_t(e * 32) << 16) + kTmemO0;
-    const bool carry = p.acc_o != nullptr;
-    int st[2] = {0, 0}, kl[2] = {0, 0};
-    for (int k = 0;; ++k) {
-        const int item = fetch_item<D, STAGES>(smem_base, k);
-        if (item < 0) break;
-        const WorkItem w = decode_item(p, item);
-        const long long bh_lin = (long long)w.b * p.Hq + w.h;
-#pragma unroll 1
-        for (int t = 0; t < kTilesPerCta; ++t) {
-            if (t * kBlockM >= w.rows) continue;            // half item: no rows in this slot
-            const int n = w.n_tile(t);
-            const int row = w.q0 + t * kBlockM + e * 32 + lane;
-            const bool row_ok = row < p.Nq;
-            uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)w.b * p.o_stride_b + (long long)w.h * p.o_stride_h +
-                             (long long)row * p.o_stride_n;
-            if (n == 0) {                                   // no visible key: zeros, lse = -inf (carry mode: nothing to fold)
-                if (!carry && row_ok) {
-#pragma unroll
-                    for (int i = 0; i < D / 8; ++i) st_global_v4(orow + 8 * i, 0u, 0u, 0u, 0u);
-                    if (p.lse != nullptr) p.lse[bh_lin * p.Nq + row] = -INFINITY;
-                }
-                continue;
-            }
-            mbar_wait(bar0 + 8u * (L::kBarLFull + t), kl[t] & 1);
-            ++kl[t];
-            float inv_l, lse_part;
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(inv_l), "=f"(lse_part)
-                         : "r"(smem_base + L::kExchOff + uint32_t(t * kBlockM + e * 32 + lane) * 8u) : "memory");
-            mbar_arrive(bar0 + 8u * (L::kBarLFree + t));
-            float wa = 0.f, wp = inv_l;                     // plain mode: O * (1/l)
-            float* arow = nullptr;
-            if (carry) {
-                // lse' = log(e^lse_acc + e^lse_part),  O' = O_acc e^(lse_acc-lse') + (O/l) e^(lse_part-lse')
-                const long long lin = bh_lin * p.acc_rows + p.acc_off + row;
-                arow = p.acc_o + lin * D;
-                wa = 1.f; wp = 0.f;
-                if (row_ok) {
-                    const float lse_acc = p.acc_lse[lin];
-                    const float mx = fmaxf(lse_acc, lse_part);
-                    if (mx != -INFINITY) {
-                        const float ea = expf(lse_acc - mx), ep = expf(lse_part - mx);
-                        const float inv = 1.0f / (ea + ep);
-                        wa = ea * inv;
-                        wp = ep * inv * inv_l;
-                        p.acc_lse[lin] = mx + logf(ea + ep);
-                    }
-                }
-            } else if (p.lse != nullptr && row_ok) {
-                p.lse[bh_lin * p.Nq + row] = lse_part;
-            }
-            mbar_wait(bar0 + 8u * (L::kBarOFull + t), (st[t] + n - 1) & 1);     // the item's last P V has retired
-            tc_fence_after();
-            const uint32_t tO = tO0 + 128u * t;
-#pragma unroll
-            for (int qq = 0; qq < D / 16; ++qq) {           // 16 columns = one 32-byte sector of the output row at a time
-                uint32_t o[16];
-                tmem_ld16(tO + 16u * qq, o);
-                tc_wait_ld();
-                if (!carry) {
-                    uint32_t hh[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        hh[i] = pack16<DT>(__uint_as_float(o[2 * i]) * wp, __uint_as_float(o[2 * i + 1]) * wp);
-                    if (row_ok) {
-                        if constexpr (OVEC32) {
-                            st_global_v8(orow + 16 * qq, hh);
-                        } else {
-                            st_global_v4(orow + 16 * qq, hh[0], hh[1], hh[2], hh[3]);
-                            st_global_v4(orow + 16 * qq + 8, hh[4], hh[5], hh[6], hh[7]);
-                        }
-                    }
-                } else if (row_ok) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float4 a = ld_global_f4(arow + 16 * qq + 4 * i);
-                        a.x = a.x * wa + __uint_as_float(o[4 * i + 0]) * wp;
-                        a.y = a.y * wa + __uint_as_float(o[4 * i + 1]) * wp;
-                        a.z = a.z * wa + __uint_as_float(o[4 * i + 2]) * wp;
-                        a.w = a.w * wa + __uint_as_float(o[4 * i + 3]) * wp;
-                        st_global_f4(arow + 16 * qq + 4 * i, a);
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(bar0 + 8u * (L::kBarOFree + t));     // O columns may be overwritten by the next item's first P V
-            st[t] += n;
-        }
     }
     tc_fence_before();
 }

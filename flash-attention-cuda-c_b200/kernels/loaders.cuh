@@ -38,40 +38,31 @@ constexpr int kHalfBytes = kBlockN * 128;   // 16 KiB: one half of a 128-row til
 //                    8-warp layout at ~2,600 clk per pair of 128-key tiles against 2,048 clk of MMAs.
 // Both layouts are compiled (template parameter SW of the kernel); the launcher picks one per problem from the measured
 // tile table (FlashAttention.cu: kTileTable).
-#ifndef FA_EPI_SOFTMAX_REGS
-#define FA_EPI_SOFTMAX_REGS 208
-#define FA_EPI_OTHER_REGS 56
-#define FA_EPI_EPILOGUE_REGS 40
-#endif
-template <int SW, int EPI = 0>
+template <int SW>
 struct KCfg {
     static constexpr int kSoftmaxWarps = SW;
     static_assert(kSoftmaxWarps == 8 || kSoftmaxWarps == 16, "8 or 16 softmax warps");
-    static_assert(EPI == 0 || SW == 8, "the epilogue warpgroup goes with the 8-warp softmax layout");
     static constexpr bool kRows16 = kSoftmaxWarps == 16;
-    static constexpr bool kEpiWarps = EPI != 0;
     static constexpr int kSoftmaxThreadsPerTile = kSoftmaxWarps * 32 / kTilesPerCta;   // arrivals per query tile on s_free / p_full / o_free
     static constexpr int kMmaWarp0 = kSoftmaxWarps;           // MMA issuer: every Q K^T (by type) / query tile 0 (by tile)
     static constexpr int kLoadWarp = kSoftmaxWarps + 1;       // TMA producer + scheduler (one thread)
     static constexpr int kMmaWarp1 = kSoftmaxWarps + 2;       // MMA issuer: every P V (by type) / query tile 1 (by tile); also allocates / frees TMEM
     static constexpr int kTmemWarp = kMmaWarp1;
-    static constexpr int kEpiWarp0 = kSoftmaxWarps + 4;       // EPI: four epilogue warps, warp kEpiWarp0 + e serves TMEM lane quarter e
-    static constexpr int kNumThreads = (kSoftmaxWarps + 4 + (kEpiWarps ? 4 : 0)) * 32;
-    static constexpr int kItemConsumers = 2 + kSoftmaxWarps + (kEpiWarps ? 4 : 0);    // warps that read every published work item
+    static constexpr int kNumThreads = (kSoftmaxWarps + 4) * 32;
     // Register split (setmaxnreg): what __launch_bounds__(kNumThreads, 1) gives every thread at launch is re-divided between
     // the softmax warps and the rest; the CTA may not hold more than it was launched with.
     //   8 warps : 168 at launch -> 256 x 216 + 128 x 72;   16 warps: 96 at launch -> 512 x 104 + 128 x 64
-    //   8 + epilogue warpgroup: 128 at launch -> 256 x 208 (softmax) + 128 x 56 (issuers / producer) + 128 x 40 (epilogue)
+    // (A fourth warpgroup that only stores O — 256 x 208 + 128 x 56 + 128 x 40 — was built and measured in round 2: with 40
+    // registers it drains TMEM 16 columns at a time, the next item's first P V waits for it, and causal N <= 2K lost 11-27 %.)
     static constexpr int kLaunchRegs = (65536 / kNumThreads) / 8 * 8;
 #ifdef FA_SOFTMAX_REGS
     static constexpr int kSoftmaxRegs = FA_SOFTMAX_REGS;
     static constexpr int kOtherRegs = FA_OTHER_REGS;
 #else
-    static constexpr int kSoftmaxRegs = kRows16 ? 104 : (kEpiWarps ? FA_EPI_SOFTMAX_REGS : 216);
-    static constexpr int kOtherRegs = kRows16 ? 64 : (kEpiWarps ? FA_EPI_OTHER_REGS : 72);
+    static constexpr int kSoftmaxRegs = kRows16 ? 104 : 216;
+    static constexpr int kOtherRegs = kRows16 ? 64 : 72;
 #endif
-    static constexpr int kEpilogueRegs = FA_EPI_EPILOGUE_REGS;       // the epilogue warpgroup (EPI only)
-    static_assert(kSoftmaxWarps * 32 * kSoftmaxRegs + 128 * kOtherRegs + (kEpiWarps ? 128 * kEpilogueRegs : 0) <= kNumThreads * kLaunchRegs,
+    static_assert(kSoftmaxWarps * 32 * kSoftmaxRegs + 128 * kOtherRegs <= kNumThreads * kLaunchRegs,
                   "register split exceeds what the CTA owns at launch");
 };
 
@@ -141,17 +132,19 @@ struct SmemLayout {
     static constexpr int kBarSchedEmpty = kBarSchedFull + 2;   // [2]    all -> TMA     : work item slot consumed
     static constexpr int kBarSFree = kBarSchedEmpty + 2;       // [2]    softmax -> MMA : S tile of query tile t copied into registers
     static constexpr int kBarOHalf = kBarSFree + 2;            // [2]    MMA -> softmax : first half (keys 0..63) of P*V of this step retired
-    static constexpr int kBarLFull = kBarOHalf + 2;            // [2]    softmax -> epilogue warps : (1/l, lse) of the item's rows are in the exchange area
-    static constexpr int kBarLFree = kBarLFull + 2;            // [2]    epilogue warps -> softmax : exchange area read
-    static constexpr int kNumBars = kBarLFree + 2;
+    static constexpr int kNumBars = kBarOHalf + 2;
     static constexpr int kSchedItemOff = kBarOff + kNumBars * 8;   // int[2]
     static constexpr int kTmemPtrOff = kSchedItemOff + 8;
-    // per query tile and row, (1 / row sum, log-sum-exp) handed from the thread that owned the row during the key loop to the
-    // thread that stores it in the epilogue (float2[2][128]): between the two warps of a lane quarter in the 16-warp layout,
-    // from the softmax warps to the epilogue warpgroup in the EPI layout
+    // 16-softmax-warp layout: per query tile and row, (1 / row sum, log-sum-exp) handed from the warp that owns the row in the
+    // 16-lane layout to the warp that stores it in the epilogue (float2[2][128])
     static constexpr int kExchOff = kTmemPtrOff + 16;
     static constexpr int kExchBytes = kTilesPerCta * kBlockM * 8;
     static constexpr int kBytes = kExchOff + kExchBytes;
+    // staged epilogue (template parameter ST of the kernel): one 128-row x 64-column output piece per query tile, in the
+    // 128B-swizzled layout a TMA store reads (16 KiB each); d = 128 pays for it with a 4-slot K/V ring
+    static constexpr int kStageOff = (kBytes + 1023) & ~1023;
+    static constexpr int kStageTileBytes = kBlockM * 128;
+    static constexpr int kBytesStaged = kStageOff + kTilesPerCta * kStageTileBytes;
     static_assert(kBytes <= 232448, "more than 227 KB of shared memory");
     // The dynamic shared-memory window of a kernel without static shared memory starts 1024-B aligned (the kernel traps if
     // it ever does not), so no alignment slack is reserved.

@@ -152,6 +152,23 @@ __device__ __forceinline__ void tma_load_4d_hint(const CUtensorMap* m, uint32_t 
           "l"(policy)
         : "memory");
 }
+// 4-D tiled STORE shared -> global (bulk async-group completion); rows / columns outside the tensor are clipped by the hardware
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every bulk group of this thread has finished READING its shared-memory source (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// every bulk group of this thread has completed (its global writes are performed)
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA) after this fence + a barrier
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 // L2 eviction policies (same encodings createpolicy would return; used as cache hints)
 static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 static constexpr uint64_t kEvictLast  = 0x14F0000000000000ull;

@@ -135,7 +135,7 @@ typedef struct {
     int stages;                /* K/V ring slots in shared memory */
     int softmax_warps;         /* 8: one score row per thread; 16: 16-lane TMEM fragments, 4 softmax warps per SM sub-partition */
     int emu_pairs_per_8;       /* of every 8 score pairs, this many take exp2 on the FMA pipe instead of MUFU.EX2 */
-    int epilogue_warps;        /* 1: a fourth warpgroup stores O while the softmax warps go on to the next work item */
+    int staged_epilogue;       /* 1: O leaves through shared memory and TMA stores (d = 128: `stages` is 4 then), 0: row-per-lane st.global */
     int issuer_by_type;        /* MMA issuer warps split by type (all QK^T / all PV) instead of by query tile */
     int cta_group;             /* 1: single-CTA tcgen05.mma (no 2-CTA variant is built) */
     float tflops;              /* measured for the bucket's representative shape (profiles/r2_tile_sweep.jsonl); 0 = not measured */

@@ -41,7 +41,7 @@ for (B, H, N, d, causal, dt) in shapes:
             for _ in range(5):
                 prof.zero_(); fn(); torch.cuda.synchronize(); cyc.append(int(prof[30].item()))
             L.fa_debug_set_profile_buffer(None)
-            print(json.dumps({"shape": f"B{B}_H{H}_N{N}_d{d}_{'c' if causal else 'nc'}", "softmax_warps": sw, "emu": emu, "epilogue_warps": epi, "half_items": half,
+            print(json.dumps({"shape": f"B{B}_H{H}_N{N}_d{d}_{'c' if causal else 'nc'}", "softmax_warps": sw, "emu": emu, "staged_epilogue": epi, "half_items": half,
                               "eager_us": round(eager * 1e3, 2), "graph_us": round(graph * 1e3, 2), "tflops_graph": round(F / graph / 1e9, 1),
                               "max_cta_cycles": min(cyc)}), flush=True)
 fa_b200.force_variant(0, 0, 0); L.fa_debug_half_items(1)

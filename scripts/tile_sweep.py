@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "flash-attention-cuda-c_b200")]
 import torch, fa_b200
 
-VARIANTS = [(8, 0, 0), (8, 0, 1), (16, 1, 0)]      # (softmax warps, exp2 pairs of 8 on the FMA pipe, epilogue warpgroup)
+VARIANTS = [(8, 0, 0), (8, 0, 1), (16, 1, 0)]      # (softmax warps, exp2 pairs of 8 on the FMA pipe, staged TMA-store epilogue)
 rounds = int(os.environ.get("FA_TS_ROUNDS", "3")); budget_ms = float(os.environ.get("FA_TS_MS", "60"))
 dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[os.environ.get("FA_TS_DTYPE", "bf16")]
 for d in (128, 64):
@@ -41,11 +41,11 @@ for d in (128, 64):
             best = None
             for vv in VARIANTS:
                 ms = sum(res[vv]) / len(res[vv])
-                rec = {"d": d, "causal": causal, "N": N, "B": B, "H": H, "dtype": str(dt).split(".")[-1], "softmax_warps": vv[0], "emu": vv[1], "epilogue_warps": vv[2],
+                rec = {"d": d, "causal": causal, "N": N, "B": B, "H": H, "dtype": str(dt).split(".")[-1], "softmax_warps": vv[0], "emu": vv[1], "staged_epilogue": vv[2],
                        "ms_mean": round(ms, 5), "ms_min": round(min(res[vv]), 5), "tflops": round(F / ms / 1e9, 1), "launches_per_round": n_launch[vv]}
                 print(json.dumps(rec), flush=True)
                 if best is None or ms < best[1]: best = (vv, ms)
-            print(json.dumps({"winner": True, "d": d, "causal": causal, "N": N, "softmax_warps": best[0][0], "emu": best[0][1], "epilogue_warps": best[0][2],
+            print(json.dumps({"winner": True, "d": d, "causal": causal, "N": N, "softmax_warps": best[0][0], "emu": best[0][1], "staged_epilogue": best[0][2],
                               "tflops": round(F / best[1] / 1e9, 1)}), flush=True)
             del q, k, v, o
 fa_b200.force_variant(0, 0, 0)
