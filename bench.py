@@ -521,15 +521,17 @@ def ring_leg(torch, dist, fa_b200, dev, rank, world):
         rec["single_gpu_tflops"] = F / t1 / 1e9
         ql, kl, vl = (sharding.zigzag_split(t, world, rank) for t in (q, k, v))
         want = sharding.zigzag_split(o_full, world, rank).float()
-        fa_b200.set_sm_reserve(4)       # room for the barrier kernels (peer) / NCCL's copy kernels (p2p) beside the persistent CTAs
-        for transport in ("peer", "p2p"):
+        # SMs the persistent attention kernel leaves free: 4 for the one-CTA barrier kernels of the peer transport, 8 for
+        # NCCL's send/recv kernels (profiles/multi/r2_ring_p2p_tune_g8.jsonl: 0-4 SMs 8.7 ms per pass, 8 SMs 6.5 ms, more is worse)
+        for transport, reserve in (("peer", 4), ("p2p", 8)):
+            fa_b200.set_sm_reserve(reserve)
             try:
                 ms = timed(lambda: sharding.ring_attention(ql, kl, vl, causal=True, transport=transport), 5)
                 out = sharding.ring_attention(ql, kl, vl, causal=True, transport=transport)
                 e = torch.tensor([(out.float() - want).abs().max().item()], device=dev, dtype=torch.float64)
                 dist.all_reduce(e, op=dist.ReduceOp.MAX)
                 rec[transport] = {"ms_per_pass": ms, "value": F / ms / 1e9, "unit": "TFLOP/s", "scaling_vs_single_gpu": t1 / ms,
-                                  "max_abs_err_vs_single_gpu": float(e.item()), "launches_per_pass": world + 1}
+                                  "max_abs_err_vs_single_gpu": float(e.item()), "launches_per_pass": world + 1, "sm_reserve": reserve}
                 if rank == 0 and "oracle_sample_max_abs_err" not in rec:
                     # rank 0 owns the last chunk of the sequence: its last 128 local rows are the global rows N-128 .. N-1
                     import numpy as np
