@@ -292,7 +292,7 @@ def run_ours(args, wl, wl_name):
 
     # ---- sustained: the same launch held for >= 0.7 s under one event pair (power-capped steady state) ------
     sustained_rec = None
-    if not ring:
+    if not ring and not args.no_extras:
         n_sus = int(min(20000, max(200, 700.0 / max(ms_per_step, 1e-3))))
         sus_sampler = ClockSampler(local)
         if rank == 0:
@@ -315,8 +315,8 @@ def run_ours(args, wl, wl_name):
     # ---- end to end: pinned host buffers through fa_fwd_host, copies inside the timed region --------------
     e2e = None
     e2e_steps = max(1, min(args.steps, 3))
-    if ring:
-        e2e = {"value": None, "error": "ring-KV keeps Q/K/V sharded and resident on the GPUs; the host-buffer path is measured on cfg3"}
+    if ring or args.no_extras:
+        e2e = {"value": None, "error": "ring-KV keeps Q/K/V sharded and resident on the GPUs; the host-buffer path is measured on cfg3" if ring else "skipped (--no-extras)"}
     else:
         dt, pcie_dt, err = -1.0, -1.0, None
         try:
@@ -390,11 +390,11 @@ def run_ours(args, wl, wl_name):
 
     # ---- ring-KV (BASELINE configs[4]) beside the sharded workload whenever there is more than one rank ----
     ring_rec = None
-    if world > 1 and not ring:
+    if world > 1 and not ring and not args.no_extras:
         ring_rec = ring_leg(torch, dist, fa_b200, dev, rank, world)
 
     small = None
-    if rank == 0 and world == 1 and not ring:
+    if rank == 0 and world == 1 and not ring and not args.no_extras:
         small = small_shapes(torch, fa_b200, dev)
 
     if rank == 0:
@@ -557,6 +557,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="profiling runs: only warm-up + the timed region (no sustained / e2e / ring / small-shape legs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -238,6 +238,15 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
         if (pub < 0) break;
         const WorkItem w = decode_item(p, item);
         if (w.n_kv > 0) {
+#ifndef FA_NO_Q_PREFETCH
+            // The Q tiles can only land once the previous item's last Q K^T has retired, and they come from HBM (each is read
+            // exactly once): start them towards L2 now, two or three key tiles early, so that the load below is an L2 hit and
+            // the tensor pipe's bubble at an item boundary shrinks by most of a DRAM round trip.
+            if (k > 0)
+                for (int t = 0; t < w.rows / kBlockM; ++t)
+#pragma unroll
+                    for (int hf = 0; hf < kHalves; ++hf) tma_prefetch_l2_4d(tmQ, hf * kHalfCols, w.q0 + t * kBlockM, w.h, w.b);
+#endif
             mbar_wait(q_empty, (kq & 1) ^ 1);      // the previous item's last Q K^T has retired
             ++kq;
             const int q_tiles = w.rows / kBlockM;

@@ -152,6 +152,11 @@ __device__ __forceinline__ void tma_load_4d_hint(const CUtensorMap* m, uint32_t 
           "l"(policy)
         : "memory");
 }
+// L2 prefetch of one box of a tiled tensor (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // 4-D tiled STORE shared -> global (bulk async-group completion); rows / columns outside the tensor are clipped by the hardware
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2, int c3) {
     asm volatile(
