@@ -195,7 +195,7 @@ const fa_tile_choice_t kTileTable[] = {
     { 64, 1,  4096,  256, 128, 8, 16, 1, 0, 0, 1,  722.2f},   // +1 % at 4K, +3 % at 8K, +6 .. +8 % from 16K
 };
 constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
-std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_half_items{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
+std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
 
 const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
     const fa_tile_choice_t* best = nullptr;
@@ -207,11 +207,42 @@ const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
 }
 
 // ---- tcgen05 path ----------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU, int ST>
+// Work-item plan of a launch: query blocks are queued as 256-row items in whole waves of max_ctas; when the remainder would
+// leave more than half of the SMs idle for a whole item, it is queued as 128-row half items instead.  Launches of many
+// waves are left alone: their tail is already short against the rest.
+struct ItemPlan { int num_q_blocks, n_full, total, max_ctas; int* counter; };
+
+// the arithmetic of the plan (host only; fa_debug_plan_counts exposes it to the CPU tests)
+void plan_counts(long long blocks, long long max_ctas, bool half_items, long long* n_full, long long* total) {
+    *n_full = blocks;
+    const long long waves = blocks / max_ctas, rem = blocks - waves * max_ctas;
+    if (half_items && waves <= 3 && rem > 0 && 2 * rem <= max_ctas) *n_full = waves * max_ctas;
+    *total = *n_full + 2 * (blocks - *n_full);
+}
+
+int plan_items(fa::FwdParams& p, cudaStream_t st, ItemPlan* plan) {
+    const int rows_per_item = fa::kTilesPerCta * fa::kBlockM;
+    plan->num_q_blocks = (p.Nq + rows_per_item - 1) / rows_per_item;
+    const long long blocks = (long long)plan->num_q_blocks * p.Hq * p.B;
+    if (blocks > 0x3fffffffLL - 4096) return fail(FA_ERR_INVALID_ARGUMENT, "too many work items (%lld)", blocks);
+    int sm_count = 0;
+    plan->counter = next_counter(st, &sm_count);
+    if (!plan->counter) return fail(FA_ERR_CUDA, "work-item counter allocation failed");
+    int max_ctas = sm_count - g_sm_reserve.load();      // SMs left free for a concurrent communication kernel
+    if (max_ctas < 1) max_ctas = 1;
+    long long n_full = 0, total = 0;
+    plan_counts(blocks, max_ctas, g_half_items.load() != 0, &n_full, &total);
+    plan->n_full = (int)n_full;
+    plan->total = (int)total;
+    plan->max_ctas = max_ctas;
+    return FA_OK;
+}
+
+template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU, int ST, int HS>
 int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, fa::FwdParams p,
-                 cudaStream_t st) {
+                 const ItemPlan& plan, cudaStream_t st) {
     using L = fa::SmemLayout<D, STAGES>;
-    auto kern = fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU, ST>;
+    auto kern = fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU, ST, HS>;
     constexpr int kSmem = ST ? L::kBytesStaged : L::kDynamicBytes;
     // the dynamic shared-memory opt-in is per device
     int dev = 0;
@@ -222,24 +253,12 @@ int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
         if (e != cudaSuccess) return fail(FA_ERR_CUDA, "cudaFuncSetAttribute(smem=%d) -> %s", kSmem, cudaGetErrorString(e));
         dev_mask.fetch_or(1ull << dev);
     }
-    const int rows_per_item = fa::kTilesPerCta * fa::kBlockM;
-    p.num_q_blocks = (p.Nq + rows_per_item - 1) / rows_per_item;
-    const long long blocks = (long long)p.num_q_blocks * p.Hq * p.B;
-    if (blocks > 0x3fffffffLL - 4096) return fail(FA_ERR_INVALID_ARGUMENT, "too many work items (%lld)", blocks);
-    int sm_count = 0;
-    p.sched_counter = next_counter(st, &sm_count);
-    if (!p.sched_counter) return fail(FA_ERR_CUDA, "work-item counter allocation failed");
-    int max_ctas = sm_count - g_sm_reserve.load();      // SMs left free for a concurrent communication kernel
-    if (max_ctas < 1) max_ctas = 1;
-    // Tail of a small launch: query blocks are queued as 256-row items in whole waves of max_ctas; when the remainder would
-    // leave more than half of the SMs idle for a whole item, it is queued as 128-row half items instead (a half item
-    // costs ~0.6 of a full one).  Launches of many waves are left alone: their tail is already short against the rest.
-    long long n_full = blocks;
-    const long long waves = blocks / max_ctas, rem = blocks - waves * max_ctas;
-    if (g_half_items.load() && waves <= 3 && rem > 0 && 2 * rem <= max_ctas) n_full = waves * max_ctas;
-    p.n_full_items = (int)n_full;
-    p.total_items = (int)(n_full + 2 * (blocks - n_full));
-    const int grid = p.total_items < max_ctas ? p.total_items : max_ctas;   // persistent: one CTA per SM
+    p.num_q_blocks = plan.num_q_blocks;
+    p.sched_counter = plan.counter;
+    p.n_full_items = plan.n_full;
+    p.total_items = plan.total;
+    p.split_half = HS;      // half items on both query-tile slots (split-KV) or on slot 0 alone
+    const int grid = p.total_items < plan.max_ctas ? p.total_items : plan.max_ctas;   // persistent: one CTA per SM
     kern<<<grid, fa::KCfg<SW>::kNumThreads, kSmem, st>>>(tq, tk, tv, to, p);
     g_launches.fetch_add(1);
     FA_CUDA(cudaGetLastError());
@@ -247,15 +266,25 @@ int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
 }
 
 // compiled variants: (softmax warps, exp2 share on the FMA pipe, staged TMA-store epilogue) = (8,0,0) (8,0,1) (16,1,0); the staged
-// epilogue takes its 32 KiB of shared memory from the K/V ring at d = 128 (4 slots instead of 5) and from spare room at d = 64
+// epilogue takes its 32 KiB of shared memory from the K/V ring at d = 128 (4 slots instead of 5) and from spare room at d = 64.
+// The two 8-warp variants exist a second time with the split-KV half-item code (HS = 1): launches whose plan has half items
+// get that build (plain mode only), all others the build without it.
 template <int D, int DT, bool OVEC32>
 int launch_variant(int sw, int emu, int stg, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
-                   const fa::FwdParams& p, cudaStream_t st) {
+                   fa::FwdParams& p, cudaStream_t st) {
     (void)emu;
+    ItemPlan plan;
+    if (int rc = plan_items(p, st, &plan)) return rc;
+    // split-KV half items: plain mode, and only when no step of the launch needs a mask (the HS kernels keep the key loop of
+    // the plain ones: a slot's key-tile numbering is not known to its softmax warps)
+    const bool hs = plan.total > plan.n_full && p.acc_o == nullptr && !p.causal && p.Nk % fa::kBlockN == 0 && g_split_half.load() != 0;
     constexpr int kStages = D == 128 ? 5 : 8;
-    if (sw == 16) return launch_sm100<D, kStages, DT, OVEC32, 16, 1, 0>(tq, tk, tv, to, p, st);
-    if (stg) return launch_sm100<D, (D == 128 ? 4 : 8), DT, OVEC32, 8, 0, 1>(tq, tk, tv, to, p, st);
-    return launch_sm100<D, kStages, DT, OVEC32, 8, 0, 0>(tq, tk, tv, to, p, st);
+    constexpr int kStagesStaged = D == 128 ? 4 : 8;
+    if (sw == 16) return launch_sm100<D, kStages, DT, OVEC32, 16, 1, 0, 0>(tq, tk, tv, to, p, plan, st);
+    if (stg) return hs ? launch_sm100<D, kStagesStaged, DT, OVEC32, 8, 0, 1, 1>(tq, tk, tv, to, p, plan, st)
+                       : launch_sm100<D, kStagesStaged, DT, OVEC32, 8, 0, 1, 0>(tq, tk, tv, to, p, plan, st);
+    return hs ? launch_sm100<D, kStages, DT, OVEC32, 8, 0, 0, 1>(tq, tk, tv, to, p, plan, st)
+              : launch_sm100<D, kStages, DT, OVEC32, 8, 0, 0, 0>(tq, tk, tv, to, p, plan, st);
 }
 
 template <int D>
@@ -592,7 +621,12 @@ int fa_debug_force_variant(int softmax_warps, int emu, int staged) {
     g_force_stg.store(staged);
     return FA_OK;
 }
-int fa_debug_half_items(int on) { g_half_items.store(on ? 1 : 0); return FA_OK; }
+int fa_debug_plan_counts(long long blocks, int max_ctas, long long* n_full, long long* total) {
+    if (blocks < 0 || max_ctas < 1 || !n_full || !total) return FA_ERR_INVALID_ARGUMENT;
+    plan_counts(blocks, max_ctas, true, n_full, total);
+    return FA_OK;
+}
+int fa_debug_half_items(int on) { g_half_items.store(on ? 1 : 0); g_split_half.store(on > 1 ? 0 : 1); return FA_OK; }   // 0: off, 1: on (split-KV), 2: on, slot 0 alone
 int fa_num_cta(int q_dim, int q_block_size) {
     if (q_dim <= 0 || q_block_size <= 0) return 0;
     return (q_dim + q_block_size - 1) / q_block_size;

@@ -6,10 +6,11 @@
 //                                                    int batchSize, int numHeads, int seqLen, float scale, bool is_causal)
 // (reference: kernels/FlashAttention.cuh:59-63), and adds the B200-native kernel the C-ABI launcher in
 // FlashAttention.cu dispatches to:
-//   fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU, ST> — warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16; OVEC32: O is
+//   fa::fwdSm100Kernel<D, STAGES, DT, OVEC32, SW, EMU, ST, HS> — warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16; OVEC32: O is
 //                                        32-byte aligned, so the epilogue may use 256-bit stores; SW: 8 or 16 softmax warps;
 //                                        EMU: share of the exponentials on the FMA pipe; ST: epilogue staged
-//                                        through shared memory and written with TMA stores)
+//                                        through shared memory and written with TMA stores; HS: half items run split-KV
+//                                        on both query-tile slots — the build small launches with a short last wave get)
 //   fa::fwdFp32Kernel<D>                — exact-fp32 CUDA-core kernel for fp32 I/O
 // The compat template is launched by the *caller* with a grid/block/shared-memory size of its own choosing
 // (reference: tests/main.cu:51-61 uses grid 1, (QT+2)*32 threads, (3QT+4R)*D*4 bytes), so it cannot take TMA
@@ -40,7 +41,7 @@ namespace fa {
 //   warp  S+2    TMEM allocator, then MMA issuer: every P V (d = 128) / everything of query tile 1 (d = 64)
 //   warp  S+3    idle (times the CTA for scripts/cycles.py when a debug profile buffer is set)
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU, int ST>
+template <int D, int STAGES, int DT, bool OVEC32, int SW, int EMU, int ST, int HS>
 __global__ void __launch_bounds__(KCfg<SW>::kNumThreads, 1)
 fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const FwdParams p) {
@@ -96,15 +97,15 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp < C::kSoftmaxWarps) {
         reg_inc<C::kSoftmaxRegs>();
         if constexpr (C::kRows16) softmaxRows16<D, STAGES, DT, OVEC32, EMU>(smem_base, tmem_base, p, warp / 8, (warp / 4) & 1);
-        else softmaxWarpgroup<D, STAGES, DT, OVEC32, EMU, ST>(smem_base, tmem_base, p, warp / 4, &tmO);
+        else softmaxWarpgroup<D, STAGES, DT, OVEC32, EMU, ST, HS>(smem_base, tmem_base, p, warp / 4, &tmO);
     } else {
         reg_dec<C::kOtherRegs>();
         if (warp == C::kMmaWarp0) {
-            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT, SW>(smem_base, tmem_base, p, 0);
-            else mmaIssuerWarp<D, STAGES, DT, SW>(smem_base, tmem_base, p, 0);
+            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT, SW, HS>(smem_base, tmem_base, p, 0);
+            else mmaIssuerWarp<D, STAGES, DT, SW, HS>(smem_base, tmem_base, p, 0);
         } else if (warp == C::kMmaWarp1) {
-            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT, SW>(smem_base, tmem_base, p, 1);
-            else mmaIssuerWarp<D, STAGES, DT, SW>(smem_base, tmem_base, p, 1);
+            if constexpr (kIssuerByType<D>) mmaTypeIssuerWarp<D, STAGES, DT, SW, HS>(smem_base, tmem_base, p, 1);
+            else mmaIssuerWarp<D, STAGES, DT, SW, HS>(smem_base, tmem_base, p, 1);
         } else if (warp == C::kLoadWarp) {
             if (lane == 0) tmaLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, p);
         }

@@ -50,7 +50,7 @@ constexpr int kNoRow = 0x3fff0000;          // first row of a query-tile slot th
 // issuer multiplied with the tile, a plain arrive when it did not (causal blocks: the early query tile stops one key
 // tile sooner) — in both cases only after it has seen the slot full, which keeps the phases in step.
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, int SW>
+template <int D, int STAGES, int DT, int SW, int HS>
 __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p, const int t) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);   // tell the compiler it is warp-uniform
     using L = SmemLayout<D, STAGES>;
@@ -142,7 +142,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
             if (elect_one_sync()) mbar_arrive_n(bar(L::kBarSFree + t), KCfg<SW>::kSoftmaxThreadsPerTile);
             __syncwarp();
         };
-        auto pv = [&](int j) {
+        auto pv = [&](int j, int it_v) {          // step j of this slot against the V tile in ring entry it_v
             const uint32_t ph = (st + j) & 1;
             // the previous item's epilogue must have read O_t out of TMEM before this item overwrites it
             if (j == 0 && ko > 0) mbar_wait(bar(L::kBarOFree + t), (ko - 1) & 1);
@@ -151,14 +151,14 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
             tc_fence_after();
             FA_PROF_MARK(2);             // waiting for P
             FA_TRACE_EV(p.prof, k, t, 1, j, 2);
-            issue_pv_half(slot_addr(it0 + 2 * j + 1), j > 0, 0, 0);
+            issue_pv_half(slot_addr(it_v), j > 0, 0, 0);
             FA_TRACE_EV(p.prof, k, t, 1, j, 3);
             FA_PROF_MARK(3);             // issue + bookkeeping
             mbar_wait(bar(L::kBarPFull + 2 * t + 1), ph);
             tc_fence_after();
             FA_PROF_MARK(2);
             FA_TRACE_EV(p.prof, k, t, 1, j, 4);
-            issue_pv_half(slot_addr(it0 + 2 * j + 1), j > 0, 1, empty_bar(it0 + 2 * j + 1));
+            issue_pv_half(slot_addr(it_v), j > 0, 1, empty_bar(it_v));
             FA_TRACE_EV(p.prof, k, t, 1, j, 5);
             FA_PROF_MARK(3);
         };
@@ -174,6 +174,37 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
 
         mbar_wait(bar(L::kBarQFull), kq & 1);
         ++kq;
+        if (HS != 0 && w.split) {
+            // Split-KV half item: both slots hold the same 128 query rows; at step s slot t multiplies with key tile
+            // jm = 2s + t and only hands the other slot's tile jo = 2s + 1 - t back.  Ring entries in order: K_jm / K_jo, V_...
+            const int steps = w.n_steps;
+            for (int sidx = 0; sidx < steps; ++sidx) {
+                const int jm = 2 * sidx + t, jo = 2 * sidx + 1 - t;
+                if (sidx < nt) {
+                    wait_full(it0 + 2 * jm);
+                    wait_s_buffer(sidx);
+                    issue_qk(slot_addr(it0 + 2 * jm), empty_bar(it0 + 2 * jm), sidx + 1 == nt);
+                } else {
+                    virtual_qk(sidx);
+                    if (nt == 0) arrive(bar(L::kBarQEmpty));      // this slot never multiplies with Q (one key tile in all)
+                }
+                if (jo < n) {
+                    wait_full(it0 + 2 * jo);
+                    arrive(empty_bar(it0 + 2 * jo));
+                    wait_full(it0 + 2 * jo + 1);
+                    arrive(empty_bar(it0 + 2 * jo + 1));
+                }
+                if (sidx < nt) {
+                    wait_full(it0 + 2 * jm + 1);
+                    pv(sidx, it0 + 2 * jm + 1);
+                }
+            }
+            st += nt;
+            sq += steps;
+            ko += nt > 0 ? 1 : 0;
+            it0 += 2 * n;
+            continue;
+        }
         wait_full(it0);
         FA_PROF_MARK(0);                 // Q + K0 arrival
         if (nt > 0) qk(0);
@@ -196,7 +227,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
             }
             wait_full(it_v);
             FA_PROF_MARK(1);
-            if (j < nt) pv(j); else arrive(empty_bar(it_v));
+            if (j < nt) pv(j, it_v); else arrive(empty_bar(it_v));
         }
         st += nt;
         sq += n;
@@ -215,7 +246,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
 // waits behind the issue of the other kind.  Same barriers and phases as mmaIssuerWarp; both roles see every K/V slot
 // full before they hand it back (commit by the role that multiplied with it, plain arrive by the other).
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, int SW>
+template <int D, int STAGES, int DT, int SW, int HS>
 __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p, const int role) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);
     using L = SmemLayout<D, STAGES>;
@@ -245,6 +276,88 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
         const int n = w.n_kv;
         if (n <= 0) continue;
         const int nts[2] = {w.n_tile0, w.n_tile1};
+
+        if (HS != 0 && w.split) {
+            // Split-KV half item (see mmaIssuerWarp): step s, slot t <-> key tile jt = 2s + t; every ring entry is used by one
+            // slot only, multiplied with by one role and handed back by both.
+            const int steps = w.n_steps;
+            if (role == 0) {
+                mbar_wait(bar(L::kBarQFull), kq & 1);
+                ++kq;
+            }
+            for (int sidx = 0; sidx < steps; ++sidx) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int jt = 2 * sidx + t;
+                    const bool act = sidx < nts[t];
+                    if (role == 0) {
+                        if (act) wait_full(it0 + 2 * jt);
+                        const int idx = (t == 0) ? sq + sidx - 1 : sq + sidx;
+                        if (idx >= 0) {
+                            mbar_wait(bar(L::kBarSFree + (1 - t)), idx & 1);
+                            tc_fence_after();
+                        }
+                        if (elect_one_sync()) {
+                            if (act) {
+                                const uint64_t a0 = desc_k_major + ((smem_base + L::kQOff + t * L::kQTileBytes) >> 4);
+                                const uint64_t b0 = desc_k_major + (slot_addr(it0 + 2 * jt) >> 4);
+#pragma unroll
+                                for (int ks = 0; ks < D / 16; ++ks) {
+                                    const uint32_t off = ((ks / 4) * kHalfBytes + (ks % 4) * 32) >> 4;
+                                    umma_ss(s_tmem, a0 + off, b0 + off, idesc_qk, ks > 0);
+                                }
+                                tc_commit(bar(L::kBarSFull + t));
+                                tc_commit(empty_bar(it0 + 2 * jt));
+                            } else {
+                                mbar_arrive_n(bar(L::kBarSFree + t), KCfg<SW>::kSoftmaxThreadsPerTile);
+                            }
+                            if (sidx + 1 == steps && t == 1) tc_commit(bar(L::kBarQEmpty));    // every Q K^T of the item has been issued
+                        }
+                        __syncwarp();
+                        if (act) {
+                            wait_full(it0 + 2 * jt + 1);
+                            arrive(empty_bar(it0 + 2 * jt + 1));
+                        }
+                    } else if (act) {
+                        wait_full(it0 + 2 * jt);
+                        arrive(empty_bar(it0 + 2 * jt));
+                        wait_full(it0 + 2 * jt + 1);
+                        const uint64_t b0 = desc_mn_major + (slot_addr(it0 + 2 * jt + 1) >> 4);
+                        const uint32_t ph = (st[t] + sidx) & 1;
+                        const uint32_t p_tmem = tmem_base + tmem_p_col(t);
+                        const uint32_t o_tmem = tmem_base + kTmemO0 + 128u * t;
+                        if (sidx == 0 && ko[t] > 0) mbar_wait(bar(L::kBarOFree + t), (ko[t] - 1) & 1);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            mbar_wait(bar(L::kBarPFull + 2 * t + half), ph);
+                            tc_fence_after();
+                            if (elect_one_sync()) {
+#pragma unroll
+                                for (int kk = 0; kk < kBlockN / 32; ++kk) {
+                                    const int ks = half * (kBlockN / 32) + kk;
+                                    umma_ts(o_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (sidx > 0 || ks > 0) ? 1u : 0u);
+                                }
+                                if (half == 1) {
+                                    tc_commit(bar(L::kBarOFull + t));
+                                    tc_commit(empty_bar(it0 + 2 * jt + 1));
+                                } else if (kSplitOFull<D>) {
+                                    tc_commit(bar(L::kBarOHalf + t));
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                st[t] += nts[t];
+                ko[t] += nts[t] > 0 ? 1 : 0;
+            }
+            sq += steps;
+            it0 += 2 * n;
+            continue;
+        }
 
         if (role == 0) {
             // ---- every Q_t K_j^T, in the order of the shared S buffer: S_0(0), S_1(0), S_0(1), ...
@@ -338,7 +451,7 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
 // epilogue (O/l -> global, optional LSE).  Persistent: loops over the published work items; the epilogue of one item
 // overlaps the next item's first Q K^T.
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32, int EMU, int ST>
+template <int D, int STAGES, int DT, bool OVEC32, int EMU, int ST, int HS>
 __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, int t, const CUtensorMap* tmO) {
     using L = SmemLayout<D, STAGES>;
     uint32_t bar0 = smem_base + L::kBarOff;
@@ -371,6 +484,9 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
         const int n = w.n_tile(t);
         // a half item has no rows for query-tile slot 1: n == 0 (no barrier traffic) and its row numbers lie past every
         // sequence, so the epilogue below writes nothing for it
+        // (Split-KV half item, HS = 1 kernels: both slots hold rows [q0, q0 + 128), slot t takes key tiles t, t+2, ... and slot 0
+        // writes the merged result.  The launcher only plans such items when no step needs a mask — non-causal, Nk a multiple
+        // of 128 — so the key loop below is untouched: the 216-register loop has no room for a second key-tile numbering.)
         const int tile_row0 = (t * kBlockM < w.rows) ? w.q0 + t * kBlockM : kNoRow;
         const int row = tile_row0 + warp_in_wg * 32 + lane;
 
@@ -421,6 +537,10 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
 #endif
             FA_PROF_MARK(1);             // tcgen05.ld of the score row
 
+            // (A warp-uniform fast path for the exactly diagonal tile — compares only in the one 32-column quarter that is
+            // lane-dependent, -inf fills for the quarters above it — was measured in round 2: the third code path over the
+            // 128-register score row costs the COMMON path 4 % at N = 8K and 14 % at 1K through register allocation, with or
+            // without skipping the masked quarters' exponentials.  Not kept; profiles/r2_cycles_diag_fastpath.jsonl.)
             if (need_mask) {
                 const int lim_c = p.causal ? (row + p.causal_off) : 0x7fffffff;
                 const int lim = min(lim_c, p.Nk - 1) - kv0;   // columns c > lim are masked
@@ -534,6 +654,71 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             l_run += (s0.x + s0.y) + (s1.x + s1.y);
         }
 
+        if (HS != 0 && w.split) {
+            // ---- split-KV half item: slot 1 hands (max, sum) to slot 0 and leaves; slot 0 merges both partial results ----
+            //   m = max(m0, m1);  l = l0 2^((m0-m)c) + l1 2^((m1-m)c);  O = (O_0 2^((m0-m)c) + O_1 2^((m1-m)c)) / l
+            // O_1 lives in the same TMEM lanes as O_0 (128 columns further), so slot 0's thread for a row reads both itself;
+            // only the two scalars cross through shared memory (double-buffered by the CTA's item counter).
+            const uint32_t xaddr = smem_base + L::kExchOff + uint32_t((k & 1) * kBlockM + warp_in_wg * 32 + lane) * 8u;
+            if (n > 0) {
+                mbar_wait(o_full, (st + n - 1) & 1);      // this slot's last P V has retired
+                tc_fence_after();
+            }
+            if (t == 1) {
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xaddr), "f"(m_run), "f"(l_run) : "memory");
+                tc_fence_before();
+                named_bar_sync(3u, 256u);
+                st += n;
+                continue;
+            }
+            named_bar_sync(3u, 256u);
+            tc_fence_after();
+            float m1, l1;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m1), "=f"(l1) : "r"(xaddr) : "memory");
+            const int n1 = w.n_tile1;
+            const float m = fmaxf(m_run, m1);
+            const float a0 = (m_run == -INFINITY) ? 0.f : ex2_approx((m_run - m) * c);
+            const float a1 = (m1 == -INFINITY || n1 == 0) ? 0.f : ex2_approx((m1 - m) * c);
+            const float l = l_run * a0 + l1 * a1;
+            const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+            const float w0 = a0 * inv, w1 = a1 * inv;
+            const int orow_i = w.q0 + warp_in_wg * 32 + lane;
+            const bool row_ok = orow_i < p.Nq;
+            uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)w.b * p.o_stride_b + (long long)w.h * p.o_stride_h +
+                             (long long)orow_i * p.o_stride_n;
+#pragma unroll 1
+            for (int q = 0; q < D / 16; ++q) {            // 16 columns = one 32-byte sector at a time (rare path: keep it small)
+                uint32_t o0[16], o1[16];
+                tmem_ld16(tO + 16u * q, o0);
+                tmem_ld16(tO + 128u + 16u * q, o1);       // with n1 == 0 the columns hold stale data; w1 == 0 discards it below
+                tc_wait_ld();
+                uint32_t hh[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float x = __uint_as_float(o0[2 * i]) * w0, y = __uint_as_float(o0[2 * i + 1]) * w0;
+                    if (n1 > 0) {
+                        x = fmaf(__uint_as_float(o1[2 * i]), w1, x);
+                        y = fmaf(__uint_as_float(o1[2 * i + 1]), w1, y);
+                    }
+                    hh[i] = pack16<DT>(x, y);
+                }
+                if (row_ok) {
+                    if constexpr (OVEC32) {
+                        st_global_v8(orow + 16 * q, hh);
+                    } else {
+                        st_global_v4(orow + 16 * q, hh[0], hh[1], hh[2], hh[3]);
+                        st_global_v4(orow + 16 * q + 8, hh[4], hh[5], hh[6], hh[7]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(o_free);                                         // both O tiles may be overwritten by the next item
+            if (n1 > 0) mbar_arrive(bar0 + 8u * (L::kBarOFree + 1));
+            if (p.lse != nullptr && row_ok)
+                p.lse[((long long)w.b * p.Hq + w.h) * p.Nq + orow_i] = (l > 0.f) ? (m * p.scale + logf(l)) : -INFINITY;
+            st += n;
+            continue;
+        }
         // ---- epilogue ----
         const bool row_ok = row < p.Nq;
         const long long row_lin = ((long long)w.b * p.Hq + w.h) * p.Nq + row;

@@ -108,6 +108,8 @@ struct FwdParams {
     int num_q_blocks;        // 256-row query blocks per (batch, head)
     int total_items;         // work items of the launch: n_full_items 256-row items, then two 128-row items for every remaining query block
     int n_full_items;        // the first n_full_items query blocks (in queue order) are one 256-row item each; the rest are split in halves
+    int split_half;          // 1: a half item runs on BOTH query-tile slots — slot t takes key tiles t, t+2, ... of the same 128 rows and
+                             //    the two partial results are merged in the epilogue (8-warp layouts, plain mode); 0: slot 0 alone
     int* sched_counter;      // device int, zero at launch and left zero by the launch: next work item = gridDim.x + atomicAdd(counter, 1)
     unsigned long long* prof; // FA_PHASE_PROFILE builds only: per-phase cycle counters (see scripts/phase_profile.py)
 };
@@ -158,9 +160,14 @@ struct WorkItem {
     int b, h, h_kv;
     int q0;        // first query row of the item
     int rows;      // 256, or 128 for a half item
-    int n_kv;      // number of 128-row key/value tiles the item visits (that of its busiest query tile)
-    int n_tile0, n_tile1;   // tiles each query tile takes part in (causal: the early tile stops one sooner)
+    int split;     // half item in split-KV mode: both slots work on rows [q0, q0 + 128), slot t on key tiles t, t+2, ...
+    int n_kv;      // number of 128-row key/value tiles the item loads (that of its busiest query tile)
+    int n_steps;   // steps of the item on the shared score buffer: n_kv, or ceil(n_kv / 2) in split-KV mode
+    int n_tile0, n_tile1;   // steps each query-tile slot takes part in (causal: the early tile stops one sooner; split: ceil / floor of n_kv / 2)
     __device__ __forceinline__ int n_tile(int t) const { return t == 0 ? n_tile0 : n_tile1; }
+    // key tile slot t multiplies with at its step s, and the first row of slot t's query tile
+    __device__ __forceinline__ int kv_tile(int t, int s) const { return split ? 2 * s + t : s; }
+    __device__ __forceinline__ int tile_row0(int t) const { return split ? q0 : q0 + t * kBlockM; }
 };
 
 // Items are numbered (batch, head)-major so that CTAs running at the same time share K/V through L2; inside a head
@@ -169,11 +176,13 @@ __device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
     WorkItem w;
     int blk = item, half = 0;
     w.rows = kTilesPerCta * kBlockM;
+    w.split = 0;
     if (item >= p.n_full_items) {
         const int r = item - p.n_full_items;
         blk = p.n_full_items + (r >> 1);
         half = r & 1;
         w.rows = kBlockM;
+        w.split = p.split_half;
     }
     const int bh = blk / p.num_q_blocks;
     const int r = blk - bh * p.num_q_blocks;
@@ -196,6 +205,12 @@ __device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
         if (t * kBlockM >= w.rows) n = 0;         // half item: query-tile slot 1 has no rows
         if (t == 0) w.n_tile0 = n; else w.n_tile1 = n;
         w.n_kv = n > w.n_kv ? n : w.n_kv;
+    }
+    w.n_steps = w.n_kv;
+    if (w.split) {      // slot 0's tile count is the item's (slot 1 was given no rows above): deal the key tiles out alternately
+        w.n_tile1 = w.n_kv / 2;
+        w.n_tile0 = w.n_kv - w.n_tile1;
+        w.n_steps = w.n_tile0;
     }
     return w;
 }
@@ -249,13 +264,13 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
 #endif
             mbar_wait(q_empty, (kq & 1) ^ 1);      // the previous item's last Q K^T has retired
             ++kq;
-            const int q_tiles = w.rows / kBlockM;
+            const int q_tiles = w.split ? kTilesPerCta : w.rows / kBlockM;    // split-KV: the same 128 rows into both Q buffers
             mbar_expect_tx(q_full, q_tiles * L::kQTileBytes);
             for (int t = 0; t < q_tiles; ++t)
 #pragma unroll
                 for (int hf = 0; hf < kHalves; ++hf)
                     tma_load_4d_hint(tmQ, smem_base + L::kQOff + t * L::kQTileBytes + hf * kHalfBytes, q_full,
-                                     hf * kHalfCols, w.q0 + t * kBlockM, w.h, w.b, kEvictFirst);
+                                     hf * kHalfCols, w.tile_row0(t), w.h, w.b, kEvictFirst);
             for (int j = 0; j < w.n_kv; ++j) {
 #pragma unroll
                 for (int kv = 0; kv < 2; ++kv, ++it) {

@@ -29,7 +29,7 @@ for (B, H, N, d, causal, dt) in shapes:
     o = torch.empty_like(q)
     F = 4.0 * B * H * N * N * d * (0.5 if causal else 1.0)
     for (sw, emu, epi) in ((8, 0, 0), (8, 0, 1), (16, 1, 0)):
-        for half in (0, 1):
+        for half in (0, 2, 1):      # no half items / half items on slot 0 alone / split-KV half items
             fa_b200.force_variant(sw, emu, epi); L.fa_debug_half_items(half)
             fn = lambda: fa_b200.attention_forward(q, k, v, causal=causal, out=o)
             eager = timeit(fn, 200)

@@ -103,3 +103,24 @@ def test_product_does_not_touch_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 for pat in (r"^\s*(from|import)\s+oracle", r"liboracle", r"oracle/", r"oracle\.", r"attention_oracle"):
                     assert not re.search(pat, txt, flags=re.M), f"{f} uses the oracle ({pat}): the product path must not"
+
+
+def test_work_item_plan_of_small_launches(L):
+    # the tail of a small launch: whole waves of 256-row items, and a remainder that would leave more than half of the SMs idle
+    # is queued as 128-row half items (two per remaining block).  Every block is covered exactly once either way.
+    ll = ctypes.c_longlong
+    L.fa_debug_plan_counts.argtypes = [ll, ctypes.c_int, ctypes.POINTER(ll), ctypes.POINTER(ll)]
+    def plan(blocks, ctas=148):
+        a, b = ll(), ll()
+        assert L.fa_debug_plan_counts(blocks, ctas, ctypes.byref(a), ctypes.byref(b)) == 0
+        return a.value, b.value
+    assert plan(192) == (148, 148 + 2 * 44)          # BASELINE configs[1]: 4 x 12 heads x 4 query blocks
+    assert plan(148) == (148, 148) and plan(296) == (296, 296)      # whole waves: nothing to split
+    assert plan(100) == (100, 100)                   # a single partial wave with more than half of the SMs busy stays whole
+    assert plan(40) == (0, 80)                       # a handful of blocks: all halves, twice as many SMs busy
+    assert plan(148 + 75) == (223, 223)              # remainder above half a wave: a full-item wave is cheaper than two half-item rounds
+    assert plan(8192) == (8192, 8192)                # many waves (config 3): left alone
+    for blocks in range(1, 700):
+        n_full, total = plan(blocks)
+        assert 0 <= n_full <= blocks and total == n_full + 2 * (blocks - n_full)
+        assert n_full % 148 == 0 or n_full == blocks

@@ -139,6 +139,32 @@ def test_many_work_items_carry_mode(d):
     assert np.abs(acc_o[b:b + 1, h:h + 1].cpu().numpy() - ref).max() <= TOL16
 
 
+@pytest.mark.parametrize("nk", [128, 384, 1024])           # 1 key tile (slot 1 gets none), odd and even tile counts
+@pytest.mark.parametrize("d,dtype", [(128, torch.bfloat16), (64, torch.float16)])
+def test_half_item_tail_split_kv(d, dtype, nk):
+    # a launch whose last wave is short: 148 query blocks as 256-row items + the rest as 128-row half items; non-causal with
+    # Nk a multiple of 128, so the half items run split-KV on both query-tile slots (slot t takes key tiles t, t+2, ...,
+    # merged in the epilogue).  176 blocks: 28 x 2 half items; the ragged Nq = 200 leaves the second half of every block with
+    # 72 valid rows.
+    B, H, nq = 8, 22, 200
+    q, k, v = _rand((B, H, nq, d), dtype, 90), _rand((B, H, nk, d), dtype, 91), _rand((B, H, nk, d), dtype, 92)
+    out, lse = fa_b200.attention_forward(q, k, v, causal=False, return_lse=True)
+    torch.cuda.synchronize()
+    o_t, lse_t = _torch_ref(q, k, v, False)
+    assert (out.float() - o_t).abs().max().item() <= TOL16
+    assert (lse - lse_t).abs().max().item() <= 2e-3
+    _oracle_slices(q, k, v, out, lse, False, [(0, 0), (B - 1, H - 1), (B - 1, H - 2)])      # the last blocks are the half items
+    # the same launch with the tail on slot 0 alone and with no half items at all gives the same answer to rounding
+    L = fa_b200.lib()
+    try:
+        for mode in (2, 0):
+            L.fa_debug_half_items(mode)
+            alt = fa_b200.attention_forward(q, k, v, causal=False)
+            assert (alt.float() - out.float()).abs().max().item() <= 1e-2
+    finally:
+        L.fa_debug_half_items(1)
+
+
 def test_many_work_items_rescale_path():
     # the lazy O rescale (row max growing by more than 2^8 along the keys) in the multi-item regime
     B, H, nq, nk, d = 5, 16, 768, 1536, 128
