@@ -212,6 +212,17 @@ const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
 // waves are left alone: their tail is already short against the rest.
 struct ItemPlan { int num_q_blocks, n_full, total, max_ctas; int* counter; };
 
+// (mul, shr) with  n / d == umulhi(n, mul) >> shr  for every 0 <= n < 2^31 and 2 <= d < 2^31 (round-up method:
+// s = ceil(log2 d), mul = ceil(2^(31+s) / d) < 2^32, shr = s - 1); d == 1 is marked with shr = 32 (fast_div returns n).
+// tests/test_abi.py checks it against integer division through fa_debug_fast_div.
+void make_fast_div(unsigned d, unsigned* mul, unsigned* shr) {
+    if (d <= 1) { *mul = 0; *shr = 32; return; }
+    unsigned s = 0;
+    while ((1ull << s) < d) ++s;
+    *mul = (unsigned)(((1ull << (31 + s)) + d - 1) / d);
+    *shr = s - 1;
+}
+
 // the arithmetic of the plan (host only; fa_debug_plan_counts exposes it to the CPU tests)
 void plan_counts(long long blocks, long long max_ctas, bool half_items, long long* n_full, long long* total) {
     *n_full = blocks;
@@ -254,6 +265,9 @@ int launch_sm100(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
         dev_mask.fetch_or(1ull << dev);
     }
     p.num_q_blocks = plan.num_q_blocks;
+    make_fast_div((unsigned)p.num_q_blocks, &p.div_qblocks_mul, &p.div_qblocks_shr);
+    make_fast_div((unsigned)p.Hq, &p.div_hq_mul, &p.div_hq_shr);
+    make_fast_div((unsigned)p.q_heads_per_kv, &p.div_group_mul, &p.div_group_shr);
     p.sched_counter = plan.counter;
     p.n_full_items = plan.n_full;
     p.total_items = plan.total;
@@ -625,6 +639,11 @@ int fa_debug_plan_counts(long long blocks, int max_ctas, long long* n_full, long
     if (blocks < 0 || max_ctas < 1 || !n_full || !total) return FA_ERR_INVALID_ARGUMENT;
     plan_counts(blocks, max_ctas, true, n_full, total);
     return FA_OK;
+}
+int fa_debug_fast_div(unsigned d, unsigned n) {      // what the kernels compute for n / d (host replica of loaders.cuh: fast_div)
+    unsigned mul = 0, shr = 0;
+    make_fast_div(d, &mul, &shr);
+    return shr >= 32u ? (int)n : (int)((((unsigned long long)n * mul) >> 32) >> shr);
 }
 int fa_debug_half_items(int on) { g_half_items.store(on ? 1 : 0); g_split_half.store(on > 1 ? 0 : 1); return FA_OK; }   // 0: off, 1: on (split-KV), 2: on, slot 0 alone
 int fa_num_cta(int q_dim, int q_block_size) {

@@ -68,6 +68,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
     const uint32_t p_tmem = tmem_base + tmem_p_col(t);
     const uint32_t o_tmem = tmem_base + kTmemO0 + 128u * t;
     FA_PROF_DECL(6);
+    FA_T2_DECL;
 
     // S_t = Q_t K^T, then s_full[t]; `then_release` != 0: also hand the K slot / the Q tiles back (commit = arrive on completion)
     auto issue_qk = [&](uint32_t k_smem, uint32_t release_bar, bool release_q) {
@@ -84,6 +85,7 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
             if (release_q) tc_commit(bar(L::kBarQEmpty));
         }
         __syncwarp();
+        FA_T2(p.prof, 2 + t, 6 + t);
     };
     // O_t (+)= P_t V_j in two halves of 4 k-steps (64 keys each): the first half can start while the softmax warpgroup
     // is still producing the second half of P.  The second half ends with o_full[t] and the release of the V slot.
@@ -119,9 +121,9 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
     int sq = 0;               // score-buffer steps so far (sum of n_kv over items; phase bookkeeping of s_free)
     int ko = 0;               // items in which this issuer's query tile had work (O hand-back bookkeeping)
     for (int k = 0;; ++k) {
-        const int item = fetch_item<D, STAGES>(smem_base, k);
+        WorkItem w;
+        const int item = fetch_item<D, STAGES>(smem_base, k, w);
         if (item < 0) break;
-        const WorkItem w = decode_item(p, item);
         const int n = w.n_kv;
         if (n <= 0) continue;
         const int nt = w.n_tile(t);
@@ -177,10 +179,12 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
         if (HS != 0 && w.split) {
             // Split-KV half item: both slots hold the same 128 query rows; at step s slot t multiplies with key tile
             // jm = 2s + t and only hands the other slot's tile jo = 2s + 1 - t back.  Ring entries in order: K_jm / K_jo, V_...
+            // As in the regular path the score tile of step s + 1 is issued BEFORE P V of step s, so that it is ready when the
+            // softmax warpgroup comes back for it (issued after, the warpgroup idled ~900 clk per step: scripts/trace_cta.py).
             const int steps = w.n_steps;
-            for (int sidx = 0; sidx < steps; ++sidx) {
-                const int jm = 2 * sidx + t, jo = 2 * sidx + 1 - t;
+            auto split_qk = [&](int sidx) {
                 if (sidx < nt) {
+                    const int jm = 2 * sidx + t;
                     wait_full(it0 + 2 * jm);
                     wait_s_buffer(sidx);
                     issue_qk(slot_addr(it0 + 2 * jm), empty_bar(it0 + 2 * jm), sidx + 1 == nt);
@@ -188,6 +192,11 @@ __device__ __forceinline__ void mmaIssuerWarp(uint32_t smem_base, uint32_t tmem_
                     virtual_qk(sidx);
                     if (nt == 0) arrive(bar(L::kBarQEmpty));      // this slot never multiplies with Q (one key tile in all)
                 }
+            };
+            split_qk(0);
+            for (int sidx = 0; sidx < steps; ++sidx) {
+                const int jm = 2 * sidx + t, jo = 2 * sidx + 1 - t;
+                if (sidx + 1 < steps) split_qk(sidx + 1);
                 if (jo < n) {
                     wait_full(it0 + 2 * jo);
                     arrive(empty_bar(it0 + 2 * jo));
@@ -270,9 +279,9 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
     int it0 = 0, kq = 0, sq = 0;
     int st[2] = {0, 0}, ko[2] = {0, 0};
     for (int k = 0;; ++k) {
-        const int item = fetch_item<D, STAGES>(smem_base, k);
+        WorkItem w;
+        const int item = fetch_item<D, STAGES>(smem_base, k, w);
         if (item < 0) break;
-        const WorkItem w = decode_item(p, item);
         const int n = w.n_kv;
         if (n <= 0) continue;
         const int nts[2] = {w.n_tile0, w.n_tile1};
@@ -476,11 +485,13 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
     asm volatile("" : "+r"(tS), "+r"(tP), "+r"(tO));
 
     FA_PROF_DECL(6);
+    FA_T2_DECL;
     int st = 0;      // key tiles this warpgroup has processed so far (barrier phase bookkeeping)
     for (int k = 0;; ++k) {
-        const int item = fetch_item<D, STAGES>(smem_base, k);
+        if (k > 0 && warp_in_wg == 0) FA_T2(p.prof, 4 + t, 40 + t);      // the previous item's epilogue is done
+        WorkItem w;
+        const int item = fetch_item<D, STAGES>(smem_base, k, w);
         if (item < 0) break;
-        const WorkItem w = decode_item(p, item);
         const int n = w.n_tile(t);
         // a half item has no rows for query-tile slot 1: n == 0 (no barrier traffic) and its row numbers lie past every
         // sequence, so the epilogue below writes nothing for it
@@ -524,6 +535,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             tc_wait_ld();
             tc_fence_before();
             mbar_arrive(s_free);         // the score row is in registers: the shared S buffer may be overwritten
+            if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 10 + t);
             FA_TRACE_EV(p.prof, k, t, 0, j, 1);
 #ifdef FA_PHASE_PROFILE
             // lag between the two warpgroups: clocks since the OTHER warpgroup last took an S tile (warp 0 of each reports)
@@ -648,12 +660,14 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(p_full1);
+            if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 20 + t);
             FA_TRACE_EV(p.prof, k, t, 0, j, 4);
             FA_PROF_MARK(4);             // store drain + arrive
 
             l_run += (s0.x + s0.y) + (s1.x + s1.y);
         }
 
+        if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 30 + t);
         if (HS != 0 && w.split) {
             // ---- split-KV half item: slot 1 hands (max, sum) to slot 0 and leaves; slot 0 merges both partial results ----
             //   m = max(m0, m1);  l = l0 2^((m0-m)c) + l1 2^((m1-m)c);  O = (O_0 2^((m0-m)c) + O_1 2^((m1-m)c)) / l
@@ -896,11 +910,11 @@ __device__ __forceinline__ void softmaxRows16(uint32_t smem_base, uint32_t tmem_
 
     int st = 0;      // key tiles this query tile has processed so far (barrier phase bookkeeping)
     for (int k = 0;; ++k) {
-        const int item = fetch_item<D, STAGES>(smem_base, k);
-        if (item < 0) break;
-        int n, j_mask;     // key tiles of this query tile; first key tile that needs the causal / tail mask (kept instead of the item's coordinates)
+        int item, n, j_mask;     // key tiles of this query tile; first key tile that needs the causal / tail mask (kept instead of the item's coordinates)
         {
-            const WorkItem w = decode_item(p, item);
+            WorkItem w;          // the decoded item from the mailbox; the two later uses (mask rows, epilogue) re-derive it from `item`
+            item = fetch_item<D, STAGES>(smem_base, k, w);
+            if (item < 0) break;
             n = w.n_tile(t);
             const int tile_row0 = w.q0 + t * kBlockM;
             // tail: kv0 + 128 > Nk  <=>  j >= Nk / 128;   causal: kv0 + 127 > tile_row0 + off  <=>  128 j > tile_row0 + off - 127

@@ -105,6 +105,10 @@ struct FwdParams {
     int causal;              // 0/1
     int causal_off;          // Nk - Nq: key j visible to query i iff j <= i + causal_off
     int q_heads_per_kv;      // Hq / Hkv
+    // Exact division of the work-item index by the three run-time divisors above with one multiply + shift each (host-made
+    // magic numbers, FastDiv): every role decodes every item, and three hardware integer divisions on one thread cost ~1,400
+    // clk at each item boundary (scripts/trace_cta.py) — 10 % of a five-step item.
+    unsigned div_qblocks_mul, div_qblocks_shr, div_hq_mul, div_hq_shr, div_group_mul, div_group_shr;
     int num_q_blocks;        // 256-row query blocks per (batch, head)
     int total_items;         // work items of the launch: n_full_items 256-row items, then two 128-row items for every remaining query block
     int n_full_items;        // the first n_full_items query blocks (in queue order) are one 256-row item each; the rest are split in halves
@@ -135,8 +139,12 @@ struct SmemLayout {
     static constexpr int kBarSFree = kBarSchedEmpty + 2;       // [2]    softmax -> MMA : S tile of query tile t copied into registers
     static constexpr int kBarOHalf = kBarSFree + 2;            // [2]    MMA -> softmax : first half (keys 0..63) of P*V of this step retired
     static constexpr int kNumBars = kBarOHalf + 2;
-    static constexpr int kSchedItemOff = kBarOff + kNumBars * 8;   // int[2]
-    static constexpr int kTmemPtrOff = kSchedItemOff + 8;
+    // work-item mailbox: two slots of 16 ints — the item index and its DECODED form (WorkItem), written by the producer one
+    // item ahead.  Decoding is ~1,000 clk of dependent single-thread arithmetic; done once by the producer, off the
+    // critical path, instead of by every role at every item boundary.
+    static constexpr int kSchedItemOff = (kBarOff + kNumBars * 8 + 15) & ~15;
+    static constexpr int kSchedSlotBytes = 64;
+    static constexpr int kTmemPtrOff = kSchedItemOff + 2 * kSchedSlotBytes;
     // 16-softmax-warp layout: per query tile and row, (1 / row sum, log-sum-exp) handed from the warp that owns the row in the
     // 16-lane layout to the warp that stores it in the epilogue (float2[2][128])
     static constexpr int kExchOff = kTmemPtrOff + 16;
@@ -152,6 +160,11 @@ struct SmemLayout {
     // it ever does not), so no alignment slack is reserved.
     static constexpr int kDynamicBytes = kBytes;
 };
+
+// n / d for 0 <= n < 2^31 with the (mul, shr) pair the host made for d (FlashAttention.cu: make_fast_div): exact
+__device__ __forceinline__ int fast_div(int n, unsigned mul, unsigned shr) {
+    return shr >= 32u ? n : int(__umulhi(unsigned(n), mul) >> shr);      // shr = 32 marks d == 1
+}
 
 // One work item: a 256-row query block of one (batch, head) — or, for the tail of a small launch, one 128-row half of
 // such a block (then only query-tile slot 0 of the CTA works; a half item costs ~0.6 of a full one, so splitting the last
@@ -184,12 +197,12 @@ __device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
         w.rows = kBlockM;
         w.split = p.split_half;
     }
-    const int bh = blk / p.num_q_blocks;
+    const int bh = fast_div(blk, p.div_qblocks_mul, p.div_qblocks_shr);
     const int r = blk - bh * p.num_q_blocks;
     const int qb = p.causal ? (p.num_q_blocks - 1 - r) : r;
-    w.b = bh / p.Hq;
+    w.b = fast_div(bh, p.div_hq_mul, p.div_hq_shr);
     w.h = bh - w.b * p.Hq;
-    w.h_kv = w.h / p.q_heads_per_kv;
+    w.h_kv = fast_div(w.h, p.div_group_mul, p.div_group_shr);
     w.q0 = qb * (kTilesPerCta * kBlockM) + half * kBlockM;
     const int n_all = (p.Nk + kBlockN - 1) / kBlockN;
     w.n_kv = 0;
@@ -215,18 +228,45 @@ __device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
     return w;
 }
 
-// Consumer side of the work-item hand-off (whole warp): returns the item index, or -1 when the queue is drained.
+// Consumer side of the work-item hand-off (whole warp): returns the item index (-1 when the queue is drained) and the decoded
+// item the producer left in the mailbox slot (12 ints, three 128-bit shared-memory loads from a warp-uniform address).
 template <int D, int STAGES>
-__device__ __forceinline__ int fetch_item(uint32_t smem_base, int k) {
+__device__ __forceinline__ int fetch_item(uint32_t smem_base, int k, WorkItem& w) {
     using L = SmemLayout<D, STAGES>;
     const uint32_t bar0 = smem_base + L::kBarOff;
     const int slot = k & 1;
     mbar_wait(bar0 + 8 * (L::kBarSchedFull + slot), (k >> 1) & 1);
-    int item;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(item) : "r"(smem_base + L::kSchedItemOff + 4 * slot) : "memory");
+    const uint32_t a = smem_base + L::kSchedItemOff + L::kSchedSlotBytes * slot;
+    int item, pad;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(item), "=r"(w.b), "=r"(w.h), "=r"(w.h_kv) : "r"(a) : "memory");
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.q0), "=r"(w.rows), "=r"(w.split), "=r"(w.n_kv) : "r"(a + 16) : "memory");
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.n_steps), "=r"(w.n_tile0), "=r"(w.n_tile1), "=r"(pad) : "r"(a + 32) : "memory");
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar0 + 8 * (L::kBarSchedEmpty + slot));
-    return __shfl_sync(0xffffffffu, item, 0);
+    return item;
+}
+
+
+// Kernel entry, before the CTA has set itself up (barriers, TMEM): the tiles the CTA's first item starts with are sent on their
+// way from HBM to L2, so that the real loads — which can only be issued ~4,000 clk later, once the barriers exist, the
+// register split is done and the item is published — are L2 hits.  Matters for launches of one or two items per CTA.
+template <int D, int STAGES>
+__device__ __forceinline__ void prefetchFirstItem(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
+                                                  const FwdParams& p) {
+    constexpr int kHalves = D / kHalfCols;
+    if (int(blockIdx.x) >= p.total_items) return;
+    const WorkItem w = decode_item(p, blockIdx.x);
+    if (w.n_kv <= 0) return;
+    for (int t = 0; t < w.rows / kBlockM; ++t)
+#pragma unroll
+        for (int hf = 0; hf < kHalves; ++hf) tma_prefetch_l2_4d(tmQ, hf * kHalfCols, w.q0 + t * kBlockM, w.h, w.b);
+    const int nj = w.n_kv < (STAGES + 1) / 2 ? w.n_kv : (STAGES + 1) / 2;
+    for (int j = 0; j < nj; ++j)
+#pragma unroll
+        for (int hf = 0; hf < kHalves; ++hf) {
+            tma_prefetch_l2_4d(tmK, hf * kHalfCols, j * kBlockN, w.h_kv, w.b);
+            tma_prefetch_l2_4d(tmV, hf * kHalfCols, j * kBlockN, w.h_kv, w.b);
+        }
 }
 
 // Producer: a single thread.  It is also the scheduler: it claims the CTA's next work item (the first one is
@@ -241,6 +281,8 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
     const uint32_t q_full = bar0 + 8 * L::kBarQFull;
     const uint32_t q_empty = bar0 + 8 * L::kBarQEmpty;
 
+    FA_T2_DECL;
+    FA_T2(p.prof, 1, 60);      // producer running
     int it = 0;      // K/V ring fills so far
     int kq = 0;      // Q loads so far
     int item = blockIdx.x;
@@ -248,10 +290,17 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
         const int slot = k & 1;
         mbar_wait(bar0 + 8 * (L::kBarSchedEmpty + slot), ((k >> 1) & 1) ^ 1);
         const int pub = item < p.total_items ? item : -1;
-        asm volatile("st.shared.s32 [%0], %1;" ::"r"(smem_base + L::kSchedItemOff + 4 * slot), "r"(pub) : "memory");
+        WorkItem w{};
+        if (pub >= 0) w = decode_item(p, item);
+        {
+            const uint32_t a = smem_base + L::kSchedItemOff + L::kSchedSlotBytes * slot;
+            asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pub), "r"(w.b), "r"(w.h), "r"(w.h_kv) : "memory");
+            asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(w.q0), "r"(w.rows), "r"(w.split), "r"(w.n_kv) : "memory");
+            asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a + 32), "r"(w.n_steps), "r"(w.n_tile0), "r"(w.n_tile1), "r"(0) : "memory");
+        }
         mbar_arrive(bar0 + 8 * (L::kBarSchedFull + slot));
+        FA_T2(p.prof, 1, 3);
         if (pub < 0) break;
-        const WorkItem w = decode_item(p, item);
         if (w.n_kv > 0) {
 #ifndef FA_NO_Q_PREFETCH
             // The Q tiles can only land once the previous item's last Q K^T has retired, and they come from HBM (each is read
@@ -262,7 +311,9 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
 #pragma unroll
                     for (int hf = 0; hf < kHalves; ++hf) tma_prefetch_l2_4d(tmQ, hf * kHalfCols, w.q0 + t * kBlockM, w.h, w.b);
 #endif
+            FA_T2(p.prof, 1, 61);      // item decoded
             mbar_wait(q_empty, (kq & 1) ^ 1);      // the previous item's last Q K^T has retired
+            FA_T2(p.prof, 1, 62);      // Q buffers free
             ++kq;
             const int q_tiles = w.split ? kTilesPerCta : w.rows / kBlockM;    // split-KV: the same 128 rows into both Q buffers
             mbar_expect_tx(q_full, q_tiles * L::kQTileBytes);
@@ -271,6 +322,7 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
                 for (int hf = 0; hf < kHalves; ++hf)
                     tma_load_4d_hint(tmQ, smem_base + L::kQOff + t * L::kQTileBytes + hf * kHalfBytes, q_full,
                                      hf * kHalfCols, w.tile_row0(t), w.h, w.b, kEvictFirst);
+            FA_T2(p.prof, 1, 4);
             for (int j = 0; j < w.n_kv; ++j) {
 #pragma unroll
                 for (int kv = 0; kv < 2; ++kv, ++it) {
@@ -279,6 +331,7 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
                     const uint32_t full = bar0 + 8 * (L::kBarKVFull + s);
                     mbar_wait(bar0 + 8 * (L::kBarKVEmpty + s), parity ^ 1);
                     mbar_expect_tx(full, L::kKVTileBytes);
+                    FA_T2(p.prof, 1, 5);
                     const CUtensorMap* tm = kv == 0 ? tmK : tmV;
 #pragma unroll
                     for (int hf = 0; hf < kHalves; ++hf)

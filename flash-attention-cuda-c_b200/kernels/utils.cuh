@@ -50,6 +50,27 @@
 #define FA_TRACE_EV(prof, k, tile, role, j, ev)
 #endif
 
+// FA_TRACE2 builds: an event log of one CTA (FA_T2_CTA, default 0) in the debug profile buffer, for launch-bound shapes
+// (scripts/trace_cta.py).  Every traced role keeps its own event counter in a register and writes (code << 48) | clock into
+// its own region of 128 slots (slot 64 + 128 * role + i): no atomics, a few cycles per event.  Roles: 0 thread 0 (1 kernel
+// entry, 2 set-up done, 50 CTA done), 1 producer (3 item published, 4 Q loads issued, 5 K/V tile issued), 2 / 3 MMA issuer of
+// slot 0 / 1 (6 / 7 Q K^T issued), 4 / 5 softmax warpgroup 0 / 1 (10 / 11 S tile taken, 20 / 21 P delivered, 30 / 31 epilogue
+// begins, 40 / 41 epilogue done).
+#ifdef FA_TRACE2
+#ifndef FA_T2_CTA
+#define FA_T2_CTA 0
+#endif
+#define FA_T2_DECL int t2_cnt_ = 0
+#define FA_T2(prof, role, code)                                                                                     \
+    do {                                                                                                            \
+        if ((prof) && blockIdx.x == FA_T2_CTA && (threadIdx.x & 31) == 0 && t2_cnt_ < 127)                            \
+            (prof)[64 + 128 * (role) + t2_cnt_++] = ((unsigned long long)(code) << 48) | ((unsigned long long)clock64() & 0xffffffffffffull); \
+    } while (0)
+#else
+#define FA_T2_DECL
+#define FA_T2(prof, role, code)
+#endif
+
 namespace fa {
 
 enum DType : int { kF32 = 0, kF16 = 1, kBF16 = 2 };

@@ -124,3 +124,16 @@ def test_work_item_plan_of_small_launches(L):
         n_full, total = plan(blocks)
         assert 0 <= n_full <= blocks and total == n_full + 2 * (blocks - n_full)
         assert n_full % 148 == 0 or n_full == blocks
+
+
+def test_fast_division_of_the_item_decode(L):
+    # every role decodes every work item: the three divisions by run-time values are multiply + shift with host-made magic
+    # numbers; exact for all 0 <= n < 2^31
+    import random
+    L.fa_debug_fast_div.argtypes = [ctypes.c_uint, ctypes.c_uint]
+    rng = random.Random(0)
+    ds = list(range(1, 300)) + [2 ** k + e for k in range(1, 31) for e in (-1, 0, 1) if 1 <= 2 ** k + e < 2 ** 31] + [rng.randrange(1, 2 ** 31) for _ in range(300)]
+    for d in ds:
+        for n in [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2 ** 31 - 1] + [rng.randrange(0, 2 ** 31) for _ in range(8)]:
+            if 0 <= n < 2 ** 31:
+                assert L.fa_debug_fast_div(d, n) == n // d, (d, n)
