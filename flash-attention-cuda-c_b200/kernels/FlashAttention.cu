@@ -186,13 +186,13 @@ int* next_counter(cudaStream_t st, int* sm_count_out) {
 // the K/V ring its fifth slot).
 const fa_tile_choice_t kTileTable[] = {
     //  d  causal n_min  block_q block_kv stages sm_warps emu staged issuer cta  tflops (first bucket of the row: N = n_min, or 512)
-    {128, 0,     0,  256, 128, 4,  8, 0, 1, 1, 1,  931.2f},   // N = 512: +10 % over direct stores, N = 1024: +1.5 %
-    {128, 0,  2048,  256, 128, 5,  8, 0, 0, 1, 1, 1159.2f},   // N >= 2K: the 5th ring slot is worth more than the staged epilogue (2-4 %)
-    {128, 1,     0,  256, 128, 5,  8, 0, 0, 1, 1,  518.3f},   // causal: direct stores at every length (staged: -0.5 .. -8 %)
-    { 64, 0,     0,  256, 128, 8,  8, 0, 1, 0, 1,  645.4f},   // N = 512: +7 %, N = 1024 (BASELINE configs[1]): +4.4 %
-    { 64, 0,  2048,  256, 128, 8, 16, 1, 0, 0, 1,  767.7f},   // MUFU-bound: 16 softmax warps + 1/8 of the exponentials on the FMA pipe, +2 .. +6 %
-    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 0, 1,  354.6f},
-    { 64, 1,  4096,  256, 128, 8, 16, 1, 0, 0, 1,  722.2f},   // +1 % at 4K, +3 % at 8K, +6 .. +8 % from 16K
+    {128, 0,     0,  256, 128, 4,  8, 0, 1, 1, 1,  918.0f},   // N = 512: +8 % over direct stores, N = 1024: +4 %
+    {128, 0,  2048,  256, 128, 5,  8, 0, 0, 1, 1, 1162.2f},   // N >= 2K: the 5th ring slot is worth more than the staged epilogue (1-3 %)
+    {128, 1,     0,  256, 128, 5,  8, 0, 0, 1, 1,  532.2f},   // causal: direct stores at every length (staged: +1.6 .. -5 %)
+    { 64, 0,     0,  256, 128, 8,  8, 0, 1, 0, 1,  651.0f},   // N = 512: +14 %, N = 1024 (BASELINE configs[1]): +3 %
+    { 64, 0,  2048,  256, 128, 8, 16, 1, 0, 0, 1,  770.8f},   // MUFU-bound: 16 softmax warps + 1/8 of the exponentials on the FMA pipe, +4.5 .. +5.4 %
+    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 0, 1,  390.3f},
+    { 64, 1,  4096,  256, 128, 8, 16, 1, 0, 0, 1,  722.8f},   // +2 % at 4K, +6 % at 8K, +5 .. +8 % from 16K
 };
 constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
 std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)

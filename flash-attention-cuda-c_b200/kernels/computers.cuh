@@ -750,6 +750,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 // could be exponentiating the next item's first score tile); the TMA store writes whole lines and costs the
                 // warps 16 st.shared.v4 per thread.  Rows past Nq are clipped by the tensor map.
                 mbar_wait(o_full, (st + n - 1) & 1);
+                if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 35);      // the last P V has retired
                 tc_fence_after();
                 const uint32_t stg = smem_base + L::kStageOff + uint32_t(t) * L::kStageTileBytes;
                 const int r_in = warp_in_wg * 32 + lane;
@@ -759,6 +760,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 for (int hf = 0; hf < D / kHalfCols; ++hf) {
                     if (leader) bulk_wait_group_read0();          // the previous store out of this piece has read it
                     named_bar_sync(1u + uint32_t(t), 128u);
+                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 37);      // staging piece free
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         uint32_t o[32];
@@ -777,8 +779,10 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                         tc_fence_before();
                         mbar_arrive(o_free);
                     }
+                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 38);      // piece written
                     fence_proxy_async_shared();
                     named_bar_sync(1u + uint32_t(t), 128u);
+                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 39);      // piece visible to TMA
                     if (leader) {
                         tma_store_4d(tmO, stg, hf * kHalfCols, tile_row0, w.h, w.b);
                         bulk_commit_group();
@@ -786,12 +790,14 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 }
             } else if (n > 0) {
                 mbar_wait(o_full, (st + n - 1) & 1);
+                if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 35);      // the last P V has retired
                 tc_fence_after();
 #pragma unroll
                 for (int q = 0; q < D / 32; ++q) {
                     uint32_t o[32];
                     tmem_ld32(tO + 32u * q, o);
                     tc_wait_ld();
+                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 36);      // chunk in registers
                     uint32_t h[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i)

@@ -247,28 +247,6 @@ __device__ __forceinline__ int fetch_item(uint32_t smem_base, int k, WorkItem& w
 }
 
 
-// Kernel entry, before the CTA has set itself up (barriers, TMEM): the tiles the CTA's first item starts with are sent on their
-// way from HBM to L2, so that the real loads — which can only be issued ~4,000 clk later, once the barriers exist, the
-// register split is done and the item is published — are L2 hits.  Matters for launches of one or two items per CTA.
-template <int D, int STAGES>
-__device__ __forceinline__ void prefetchFirstItem(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
-                                                  const FwdParams& p) {
-    constexpr int kHalves = D / kHalfCols;
-    if (int(blockIdx.x) >= p.total_items) return;
-    const WorkItem w = decode_item(p, blockIdx.x);
-    if (w.n_kv <= 0) return;
-    for (int t = 0; t < w.rows / kBlockM; ++t)
-#pragma unroll
-        for (int hf = 0; hf < kHalves; ++hf) tma_prefetch_l2_4d(tmQ, hf * kHalfCols, w.q0 + t * kBlockM, w.h, w.b);
-    const int nj = w.n_kv < (STAGES + 1) / 2 ? w.n_kv : (STAGES + 1) / 2;
-    for (int j = 0; j < nj; ++j)
-#pragma unroll
-        for (int hf = 0; hf < kHalves; ++hf) {
-            tma_prefetch_l2_4d(tmK, hf * kHalfCols, j * kBlockN, w.h_kv, w.b);
-            tma_prefetch_l2_4d(tmV, hf * kHalfCols, j * kBlockN, w.h_kv, w.b);
-        }
-}
-
 // Producer: a single thread.  It is also the scheduler: it claims the CTA's next work item (the first one is
 // blockIdx.x, later ones come from a global atomic counter), publishes it to the other roles one item ahead, then
 // streams that item's tiles: Q tiles once, then K_j, V_j for j = 0..n_kv-1 through the ring.
