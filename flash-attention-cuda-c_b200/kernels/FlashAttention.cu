@@ -71,14 +71,15 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [B, H, N, d] tensor with element strides (sb, sh, sn, 1); box = 64 columns x 128 rows, 128B swizzle.
+// [B, H, N, d] tensor with element strides (sb, sh, sn, 1); box = 64 columns x box_rows rows (128 for the tile loads, 32 for the
+// per-warp stores of the staged epilogue), 128B swizzle.
 // Encoding a map is a pure function of (base, dtype, shape, strides), so the last few are kept per host thread: a caller
 // that launches the same tensors again (a decode loop, a benchmark, a CUDA-graph-less training step) pays the three driver
 // calls once.  Launch-bound shapes (BASELINE configs[1]: one 20 us kernel) are where this shows.
 struct MapKey {
-    const void* base; int dtype, B, H, N, d; long long sb, sh, sn;
+    const void* base; int dtype, B, H, N, d, box_rows; long long sb, sh, sn;
     bool operator==(const MapKey& o) const {
-        return base == o.base && dtype == o.dtype && B == o.B && H == o.H && N == o.N && d == o.d && sb == o.sb && sh == o.sh && sn == o.sn;
+        return base == o.base && dtype == o.dtype && B == o.B && H == o.H && N == o.N && d == o.d && box_rows == o.box_rows && sb == o.sb && sh == o.sh && sn == o.sn;
     }
 };
 struct MapCache {
@@ -91,8 +92,8 @@ struct MapCache {
 thread_local MapCache g_maps;
 
 int make_tile_map(CUtensorMap* m, const void* base, int dtype, int B, int H, int N, int d, long long sb, long long sh,
-                  long long sn) {
-    const MapKey key{base, dtype, B, H, N, d, sb, sh, sn};
+                  long long sn, int box_rows = fa::kBlockN) {
+    const MapKey key{base, dtype, B, H, N, d, box_rows, sb, sh, sn};
     for (int i = 0; i < MapCache::kEntries; ++i)
         if (g_maps.valid[i] && g_maps.key[i] == key) { *m = g_maps.map[i]; return FA_OK; }
     EncodeTiledFn enc = get_encode_fn();
@@ -103,7 +104,7 @@ int make_tile_map(CUtensorMap* m, const void* base, int dtype, int B, int H, int
     // A size-1 dimension's stride is never used for addressing but must still be a legal value.
     if (H == 1) strides[1] = strides[0] * (cuuint64_t)N;
     if (B == 1) strides[2] = strides[1] * (cuuint64_t)H;
-    cuuint32_t box[4] = {(cuuint32_t)fa::kHalfCols, (cuuint32_t)fa::kBlockN, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)fa::kHalfCols, (cuuint32_t)box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -398,7 +399,7 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     // every output row to start 32-byte aligned (carry mode does not write O at all)
     CUtensorMap to = tq;
     if (stg && sw == 8) {
-        if (int rc = make_tile_map(&to, O, dtype, B, Hq, Nq, d, s[9], s[10], s[11])) return rc;
+        if (int rc = make_tile_map(&to, O, dtype, B, Hq, Nq, d, s[9], s[10], s[11], 32)) return rc;      // one store per warp: 64 columns x 32 rows
     }
     const bool v32 = !carry && reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0;
     const bool bf = dtype == FA_DTYPE_BF16;

@@ -744,49 +744,57 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (long long)w.b * p.o_stride_b + (long long)w.h * p.o_stride_h +
                              (long long)row * p.o_stride_n;
             if (ST != 0 && n > 0) {
-                // Staged epilogue: O / l -> this tile's 16 KiB piece of shared memory (128 rows x 64 columns, the 128B-swizzled
-                // layout of the TMA box) -> one TMA store per 64 columns.  A row-per-lane st.global touches 32 different lines
-                // per instruction (1,024 sector writes per tile, which the LSU takes ~1,000 clk to drain while the warpgroup
-                // could be exponentiating the next item's first score tile); the TMA store writes whole lines and costs the
-                // warps 16 st.shared.v4 per thread.  Rows past Nq are clipped by the tensor map.
+                // Staged epilogue, one warp at a time: every warp packs its 32 rows x 64 columns of O / l, writes them into
+                // ITS 4 KiB slice of the tile's staging piece (128B-swizzled, the layout of a TMA box of 64 columns x 32 rows)
+                // and lane 0 issues the TMA store of that slice — only warp-level synchronisation, no CTA barrier.  Rows
+                // past Nq are clipped by the tensor map.  Why: a row-per-lane st.global touches 32 different lines per
+                // instruction, 1,024 sector writes per tile, which the SM's load/store path accepts at ~2 clk each: the
+                // softmax warpgroup stood 2,200-2,900 clk in its epilogue at every item boundary (scripts/trace_cta.py).
+                // The first version of this path (one 16 KiB piece per tile, CTA-level named barriers, one TMA store per 64
+                // columns) needed 2,300-2,750 clk at d = 128: ~1,000 of them waiting for the first half's store to finish
+                // reading the piece.  Here the second half is loaded and packed BEFORE that wait, and a 4 KiB store drains fast.
                 mbar_wait(o_full, (st + n - 1) & 1);
                 if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 35);      // the last P V has retired
                 tc_fence_after();
                 const uint32_t stg = smem_base + L::kStageOff + uint32_t(t) * L::kStageTileBytes;
                 const int r_in = warp_in_wg * 32 + lane;
                 const uint32_t srow = stg + uint32_t(r_in) * 128u;
-                const bool leader = (threadIdx.x & 127) == 0;
+                const uint32_t slice = stg + uint32_t(warp_in_wg) * (32u * 128u);
+                // TMEM loads run one 32-column chunk ahead: the load of the next chunk is in flight while this one is packed,
+                // written to the slice, fenced and handed to TMA.
+                constexpr int kChunks = D / 32;
+                uint32_t o[32];
+                tmem_ld32(tO, o);
 #pragma unroll
                 for (int hf = 0; hf < D / kHalfCols; ++hf) {
-                    if (leader) bulk_wait_group_read0();          // the previous store out of this piece has read it
-                    named_bar_sync(1u + uint32_t(t), 128u);
-                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 37);      // staging piece free
+                    uint32_t pkd[32];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        uint32_t o[32];
-                        tmem_ld32(tO + 64u * hf + 32u * q, o);
                         tc_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {                 // 16-byte chunk 4q + i of the row, XOR-swizzled by row % 8
-                            uint32_t hw[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                hw[e] = pack16<DT>(__uint_as_float(o[8 * i + 2 * e]) * inv_l, __uint_as_float(o[8 * i + 2 * e + 1]) * inv_l);
-                            st_shared_v4(srow + (uint32_t((4 * q + i) ^ (r_in & 7)) << 4), hw[0], hw[1], hw[2], hw[3]);
-                        }
+                        for (int i = 0; i < 16; ++i)
+                            pkd[16 * q + i] = pack16<DT>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+                        if (2 * hf + q + 1 < kChunks) tmem_ld32(tO + 32u * uint32_t(2 * hf + q + 1), o);
                     }
                     if (hf == D / kHalfCols - 1) {                    // O is out of TMEM: the next item's first P V may overwrite it
                         tc_fence_before();
                         mbar_arrive(o_free);
                     }
-                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 38);      // piece written
+                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 36);      // half packed in registers
+                    if (lane == 0) bulk_wait_group_read0();           // this warp's previous store has read the slice
+                    __syncwarp();
+                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 37);      // slice free
+#pragma unroll
+                    for (int cidx = 0; cidx < 8; ++cidx)              // 16-byte chunk cidx of the row, XOR-swizzled by row % 8
+                        st_shared_v4(srow + (uint32_t(cidx ^ (r_in & 7)) << 4), pkd[4 * cidx], pkd[4 * cidx + 1], pkd[4 * cidx + 2], pkd[4 * cidx + 3]);
+                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 38);      // slice written
                     fence_proxy_async_shared();
-                    named_bar_sync(1u + uint32_t(t), 128u);
-                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 39);      // piece visible to TMA
-                    if (leader) {
-                        tma_store_4d(tmO, stg, hf * kHalfCols, tile_row0, w.h, w.b);
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(tmO, slice, hf * kHalfCols, tile_row0 + warp_in_wg * 32, w.h, w.b);
                         bulk_commit_group();
                     }
+                    if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 39);      // slice handed to TMA
                 }
             } else if (n > 0) {
                 mbar_wait(o_full, (st + n - 1) & 1);
@@ -870,7 +878,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
         st += n;
     }
     if ((threadIdx.x & 31) == 0) FA_PROF_FLUSH(p.prof, 0, 6);
-    if (ST != 0 && (threadIdx.x & 127) == 0) bulk_wait_group0();     // this thread's TMA stores have landed before the CTA exits
+    if (ST != 0 && lane == 0) bulk_wait_group0();     // this warp's TMA stores have landed before the CTA exits
     tc_fence_before();
 }
 
