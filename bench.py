@@ -99,17 +99,38 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms from the last warm-up steps through the timed region
-    (the timed region of the default run is < 0.1 s, so the sampler is started during warm-up to be sure it is
-    already delivering samples under load when timing starts)."""
+    """SM clock, power and clock-event reasons of one GPU, sampled in-process through NVML every ~2 ms by a thread, each
+    sample time-stamped; `stop(window)` reports the median over the samples that fall INSIDE the timed region (the GPU is busy
+    for all of it by construction), plus every sample's median.  The default timed region is ~70 ms: nvidia-smi's own loop
+    (-lms) delivers 3-4 samples in that time and its power reading lags by more than the region, so neither its clock nor
+    a power threshold can tell "under load" there.  Falls back to an nvidia-smi -lms 20 subprocess (power-threshold
+    classification: >= half of the enforced limit) when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
          "enforced.power.limit")
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.nv, self.stop_flag, self.thread = gpu_index, [], None, None, False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                ent = [e.strip() for e in vis.split(",") if e.strip()]
+                if self.idx < len(ent) and ent[self.idx].isdigit():
+                    phys = int(ent[self.idx])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = (pynvml, h)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -117,13 +138,50 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nv
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        bits = [(n, getattr(nv, a, None) or getattr(nv, b, 0)) for n, a, b in names]
+        while not self.stop_flag:
+            try:
+                t = time.perf_counter()
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append((t, mhz, watts, tuple(n for n, bit in bits if mask & bit)))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) in time.perf_counter() seconds: the timed region."""
+        if self.nv is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            rows = list(self.rows)
+            thr = 0.5 * self.limit
+            if window is not None:
+                load = [r for r in rows if window[0] <= r[0] <= window[1]]
+                how = "samples time-stamped inside the timed region"
+            else:
+                load = [r for r in rows if r[2] >= thr]
+                how = "samples drawing >= half of the enforced power limit"
+            reasons = sorted({n for r in load for n in r[3]})
+            return {"sm_mhz": statistics.median([r[1] for r in load]) if load else None,
+                    "sm_mhz_all_samples": statistics.median([r[1] for r in rows]) if rows else None,
+                    "sm_mhz_min_under_load": min(r[1] for r in load) if load else None, "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max((r[2] for r in rows), default=None), "power_limit_w": self.limit,
+                    "samples": len(rows), "samples_under_load": len(load), "under_load_means": how, "source": "NVML, 2 ms poll",
+                    "reasons": reasons, "reasons_any_sample": sorted({n for r in rows for n in r[3]})}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"]}
         time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons, power, limit = [], [], set(), [], None
@@ -144,7 +202,8 @@ class ClockSampler:
                 "sm_mhz_all_samples": statistics.median(sm) if sm else None,
                 "sm_mhz_min_under_load": min(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None, "power_limit_w": limit, "load_threshold_w": thr,
-                "samples": len(sm), "samples_under_load": len(load), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_under_load": len(load), "under_load_means": "samples drawing >= half of the enforced power limit",
+                "source": "nvidia-smi -lms 20", "reasons": sorted(reasons)}
 
 
 def cpu_attention_sample(N, d, causal, heads, torch):
@@ -273,7 +332,7 @@ def run_ours(args, wl, wl_name):
     # the K steps as ONE device-timed region (first launch to last retirement, gaps between launches included); with an L2
     # flush between steps the flush writes are not part of a step, so the per-step event times are summed instead
     total_ms = ev0.elapsed_time(ev1) if flush is None else sum(kernel_ms)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop((t_wall0, t_wall0 + t_wall)) if rank == 0 else None
     tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -301,13 +360,15 @@ def run_ours(args, wl, wl_name):
             step()
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_sus0 = time.perf_counter()
         s0.record()
         for _ in range(n_sus):
             step()
         s1.record()
         barrier()
+        t_sus1 = time.perf_counter()
         sus_ms = reduce_max(s0.elapsed_time(s1)) / n_sus
-        sus_clocks = sus_sampler.stop() if rank == 0 else None
+        sus_clocks = sus_sampler.stop((t_sus0, t_sus1)) if rank == 0 else None
         sustained_rec = {"launches": n_sus, "ms_per_step": sus_ms, "value": F * world / (sus_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                          "per_gpu": F / (sus_ms * 1e-3) / 1e12, "clocks": sus_clocks,
                          "note": "same launch back to back under one CUDA-event pair, max over ranks; L2 not flushed (inputs > L2 for the default workload)"}

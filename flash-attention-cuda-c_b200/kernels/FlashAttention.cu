@@ -177,23 +177,22 @@ int* next_counter(cudaStream_t st, int* sm_count_out) {
 // ---- measured tile table -----------------------------------------------------------------------------
 // Stands where the reference's calculateSizeBlockQ / calculateSizeBlockKV sketch register- and L2-driven formulas and then
 // return 64 (reference: helpers.hpp:8-30): per (head dim, causal, key-length bucket) the kernel variant that measured
-// fastest on B200 (scripts/tile_sweep.py -> profiles/r2_tile_sweep.jsonl: 28 shapes x the three compiled variants, launches
-// held back to back under the power cap; `tflops` is that run's figure).  fp16 takes the bf16 rows (same cycle counts).
+// fastest on B200 (scripts/tile_sweep.py -> profiles/r2_tile_sweep.jsonl: 28 shapes x the three compiled variants, six
+// interleaved rounds of 250 ms of back-to-back launches each under the power cap; `tflops` is that run's figure).  fp16 takes the bf16 rows (same cycle counts).
 // Tile geometry is the same in every row — 256 query rows per work item (2 x 128-row MMA tiles ping-ponged through the tensor
 // pipe), 128 key rows per pipeline stage, the whole TMEM and shared memory of an SM, 1-CTA MMAs — because the sweeps that
 // varied it lost: 64-key steps run the SS MMA at half rate, and no 2-CTA variant is built.  What varies is the softmax
 // layout (8 warps x one row per thread / 16 warps x 16-lane fragments), the share of exponentials moved to the FMA pipe,
-// and how O leaves the SM (row-per-lane st.global, or staged through shared memory + TMA stores, which at d = 128 costs
-// the K/V ring its fifth slot).
+// and how O leaves the SM (row-per-lane st.global, or staged per warp through shared memory + TMA stores, which at d = 128
+// costs the K/V ring its fifth slot and still wins).
 const fa_tile_choice_t kTileTable[] = {
     //  d  causal n_min  block_q block_kv stages sm_warps emu staged issuer cta  tflops (first bucket of the row: N = n_min, or 512)
-    {128, 0,     0,  256, 128, 4,  8, 0, 1, 1, 1,  918.0f},   // N = 512: +8 % over direct stores, N = 1024: +4 %
-    {128, 0,  2048,  256, 128, 5,  8, 0, 0, 1, 1, 1162.2f},   // N >= 2K: the 5th ring slot is worth more than the staged epilogue (1-3 %)
-    {128, 1,     0,  256, 128, 5,  8, 0, 0, 1, 1,  532.2f},   // causal: direct stores at every length (staged: +1.6 .. -5 %)
-    { 64, 0,     0,  256, 128, 8,  8, 0, 1, 0, 1,  651.0f},   // N = 512: +14 %, N = 1024 (BASELINE configs[1]): +3 %
-    { 64, 0,  2048,  256, 128, 8, 16, 1, 0, 0, 1,  770.8f},   // MUFU-bound: 16 softmax warps + 1/8 of the exponentials on the FMA pipe, +4.5 .. +5.4 %
-    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 0, 1,  390.3f},
-    { 64, 1,  4096,  256, 128, 8, 16, 1, 0, 0, 1,  722.8f},   // +2 % at 4K, +6 % at 8K, +5 .. +8 % from 16K
+    {128, 0,     0,  256, 128, 4,  8, 0, 1, 1, 1,  867.3f},   // staged epilogue at every length: +5.4 % at N = 512, +2.9 % at 2K, +0.9 % at 8K, +0.6 % at 32K
+    {128, 1,     0,  256, 128, 4,  8, 0, 1, 1, 1,  527.6f},   // causal: +1.2 % at 512, +2.0 % at 1K, +1.3 % at 2K, +0.3 % at 8K (the fourth ring slot is enough)
+    { 64, 0,     0,  256, 128, 8,  8, 0, 1, 0, 1,  642.5f},   // N = 512: +5.7 %, N = 1024 (BASELINE configs[1]): +3.0 %, 2K: +1.6 %
+    { 64, 0,  4096,  256, 128, 8, 16, 1, 0, 0, 1,  807.8f},   // MUFU-bound: 16 softmax warps + 1/8 of the exponentials on the FMA pipe, +1.4 .. +2.1 %
+    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 0, 1,  389.2f},   // staged: -1.5 % at 512, equal from 1K to 4K
+    { 64, 1,  8192,  256, 128, 8, 16, 1, 0, 0, 1,  783.7f},   // +0.8 % at 8K, +1.3 % at 16K, +2.0 % at 32K
 };
 constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
 std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
