@@ -96,9 +96,11 @@ def lib() -> ctypes.CDLL:
         L.fa_version.restype = ctypes.c_char_p
         L.fa_launch_count.restype = ll
         _lib = L
-        if os.environ.get("FA_FORCE_VARIANT"):     # tuning / parity runs of one compiled variant: "softmax_warps,emu"
-            sw, emu, epi = (int(x) for x in (os.environ["FA_FORCE_VARIANT"] + ",0").split(",")[:3])
+        if os.environ.get("FA_FORCE_VARIANT"):     # tuning / parity runs of one compiled variant: "softmax_warps,emu,staged[,cta_group]"
+            sw, emu, epi, cg = (int(x) for x in (os.environ["FA_FORCE_VARIANT"] + ",0,0").split(",")[:4])
             L.fa_debug_force_variant(sw, emu, epi)
+            if cg and hasattr(L, "fa_debug_force_cta_group"):
+                L.fa_debug_force_cta_group(cg)
     return _lib
 
 
@@ -225,9 +227,13 @@ def choose_tile(d, dtype_code, causal, nq, nk):
     return out.as_dict()
 
 
-def force_variant(softmax_warps=0, emu=0, staged=0):
-    """A/B tooling: run every following launch with this kernel variant (0 = back to the tile table)."""
+def force_variant(softmax_warps=0, emu=0, staged=0, cta_group=0):
+    """A/B tooling: run every following launch with this kernel variant (0 = back to the tile table); cta_group 2 = the
+    CTA-pair kernel wherever it exists (d = 128, 8 softmax warps)."""
     _check(lib().fa_debug_force_variant(int(softmax_warps), int(emu), int(staged)), "fa_debug_force_variant")
+    if hasattr(lib(), "fa_debug_force_cta_group"):
+        lib().fa_debug_force_cta_group.argtypes = [ctypes.c_int]
+        _check(lib().fa_debug_force_cta_group(int(cta_group)), "fa_debug_force_cta_group")
 
 
 def set_sm_reserve(sms: int):

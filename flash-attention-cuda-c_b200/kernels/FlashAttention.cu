@@ -195,7 +195,7 @@ const fa_tile_choice_t kTileTable[] = {
     { 64, 1,  8192,  256, 128, 8, 16, 1, 0, 0, 1,  783.7f},   // +0.8 % at 8K, +1.3 % at 16K, +2.0 % at 32K
 };
 constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
-std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
+std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_force_cg{0}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
 
 const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
     const fa_tile_choice_t* best = nullptr;
@@ -301,6 +301,56 @@ int launch_variant(int sw, int emu, int stg, const CUtensorMap& tq, const CUtens
               : launch_sm100<D, kStages, DT, OVEC32, 8, 0, 0, 0>(tq, tk, tv, to, p, plan, st);
 }
 
+// CTA-pair kernel (d = 128, 8 softmax warps): clusters of two CTAs, 512-row work items, one claim per pair.
+constexpr int kPairStages = 6;      // 16 KiB ring slots: three K halves + three V halves in flight
+template <int DT, bool OVEC32, int ST>
+int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMap& tv, const CUtensorMap& to, fa::FwdParams p, cudaStream_t st) {
+    constexpr int D = 128;
+    using L = fa::SmemLayout<D, kPairStages, 2>;
+    auto kern = fa::fwdSm100PairKernel<D, kPairStages, DT, OVEC32, ST>;
+    constexpr int kSmem = ST ? L::kBytesStaged : L::kDynamicBytes;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static std::atomic<unsigned long long> dev_mask{0};
+    static std::atomic<int> max_pairs_dev[64];
+    if (!(dev_mask.load() & (1ull << dev))) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return fail(FA_ERR_CUDA, "cudaFuncSetAttribute(pair kernel, smem=%d) -> %s", kSmem, cudaGetErrorString(e));
+        // how many pairs the device can hold at once (an SM whose TPC partner is unavailable cannot take one)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * 128);
+        cfg.blockDim = dim3(fa::KCfg<8>::kNumThreads);
+        cfg.dynamicSmemBytes = kSmem;
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess || n < 1) return fail(FA_ERR_CUDA, "cudaOccupancyMaxActiveClusters(pair kernel) -> %s (%d)", cudaGetErrorString(e), n);
+        max_pairs_dev[dev & 63].store(n);
+        dev_mask.fetch_or(1ull << dev);
+    }
+    const int num_q_blocks = (p.Nq + fa::kPairRows - 1) / fa::kPairRows;
+    const long long items = (long long)num_q_blocks * p.Hq * p.B;
+    if (items > 0x3fffffffLL - 4096) return fail(FA_ERR_INVALID_ARGUMENT, "too many work items (%lld)", items);
+    int sm_count = 0;
+    int* counter = next_counter(st, &sm_count);
+    if (!counter) return fail(FA_ERR_CUDA, "work-item counter allocation failed");
+    int max_pairs = max_pairs_dev[dev & 63].load();
+    const int by_reserve = (sm_count - g_sm_reserve.load()) / 2;
+    if (by_reserve < max_pairs) max_pairs = by_reserve;
+    if (max_pairs < 1) max_pairs = 1;
+    p.num_q_blocks = num_q_blocks;
+    make_fast_div((unsigned)p.num_q_blocks, &p.div_qblocks_mul, &p.div_qblocks_shr);
+    make_fast_div((unsigned)p.Hq, &p.div_hq_mul, &p.div_hq_shr);
+    make_fast_div((unsigned)p.q_heads_per_kv, &p.div_group_mul, &p.div_group_shr);
+    p.sched_counter = counter;
+    p.n_full_items = p.total_items = (int)items;
+    p.split_half = 0;
+    const int pairs = items < max_pairs ? (int)items : max_pairs;
+    kern<<<2 * pairs, fa::KCfg<8>::kNumThreads, kSmem, st>>>(tq, tk64, tv, to, p);
+    g_launches.fetch_add(1);
+    FA_CUDA(cudaGetLastError());
+    return FA_OK;
+}
+
 template <int D>
 int launch_fp32(const fa::Fp32Params& p, cudaStream_t st) {
     using S = fa::Fp32Smem<D>;
@@ -402,6 +452,19 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     }
     const bool v32 = !carry && reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0;
     const bool bf = dtype == FA_DTYPE_BF16;
+    int cg = tc ? tc->cta_group : 1;
+    if (g_force_cg.load()) cg = g_force_cg.load();
+    if (cg == 2 && d == 128 && sw == 8) {
+        // CTA pairs: each CTA loads 64 of a K tile's 128 keys (its own tensor map: 64-row boxes) and 64 of a V tile's columns
+        CUtensorMap tk64;
+        if (int rc = make_tile_map(&tk64, K, dtype, B, Hkv, Nk, d, s[3], s[4], s[5], 64)) return rc;
+        if (stg) {
+            if (v32) return bf ? launch_pair<fa::kBF16, true, 1>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, true, 1>(tq, tk64, tv, to, p, st);
+            return bf ? launch_pair<fa::kBF16, false, 1>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, false, 1>(tq, tk64, tv, to, p, st);
+        }
+        if (v32) return bf ? launch_pair<fa::kBF16, true, 0>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, true, 0>(tq, tk64, tv, to, p, st);
+        return bf ? launch_pair<fa::kBF16, false, 0>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, false, 0>(tq, tk64, tv, to, p, st);
+    }
     if (d == 128) {
         if (v32) return bf ? launch_variant<128, fa::kBF16, true>(sw, emu, stg, tq, tk, tv, to, p, st) : launch_variant<128, fa::kF16, true>(sw, emu, stg, tq, tk, tv, to, p, st);
         return bf ? launch_variant<128, fa::kBF16, false>(sw, emu, stg, tq, tk, tv, to, p, st) : launch_variant<128, fa::kF16, false>(sw, emu, stg, tq, tk, tv, to, p, st);
@@ -633,6 +696,12 @@ int fa_debug_force_variant(int softmax_warps, int emu, int staged) {
     g_force_sw.store(softmax_warps);
     g_force_emu.store(emu);
     g_force_stg.store(staged);
+    return FA_OK;
+}
+// 0 = as the tile table says, 1 = 1-CTA kernels, 2 = the CTA-pair kernel wherever it exists (d = 128, 8 softmax warps)
+int fa_debug_force_cta_group(int cta_group) {
+    if (cta_group < 0 || cta_group > 2) return FA_ERR_INVALID_ARGUMENT;
+    g_force_cg.store(cta_group);
     return FA_OK;
 }
 int fa_debug_plan_counts(long long blocks, int max_ctas, long long* n_full, long long* total) {

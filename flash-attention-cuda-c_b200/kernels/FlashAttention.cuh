@@ -141,6 +141,105 @@ fwdSm100Kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair kernel (d = 128): clusters of two CTAs on the two SMs of a TPC, tcgen05 cta_group::2.  A pair works on 512-row
+// query blocks; every MMA covers 256 query rows (128 in each CTA's TMEM) against a 128-key tile of which each CTA loads, holds
+// and reads only half (K: 64 of the keys; V: 64 of the d columns).  Per CTA and step that is 32 KiB instead of 64 KiB of
+// L2 -> shared-memory traffic and 128 KiB instead of 192 KiB of operand reads by the tensor core; the warp roles, the TMEM map
+// and the softmax are those of fwdSm100Kernel.  The MMA issuer warps work in the leader (even) CTA only.
+//   Why: on a power-capped B200 the step time in CYCLES does not depend on the K/V traffic at all, but the clock does — with
+//   the K/V loads removed (wrong results, same instruction stream) the same kernel sustains 7 % more TFLOP/s, with half of
+//   them 2.5 % more (profiles/r2_energy_kv_traffic.log).
+// ------------------------------------------------------------------------------------------------
+template <int D, int STAGES, int DT, bool OVEC32, int ST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KCfg<8>::kNumThreads, 1)
+fwdSm100PairKernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const FwdParams p) {
+    using L = SmemLayout<D, STAGES, 2>;
+    using C = KCfg<8>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if ((smem_base & 1023u) != 0) __trap();
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + L::kTmemPtrOff);
+
+    const int warp = threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+
+    if (warp == C::kLoadWarp && lane == 0) {
+        // arrival counts: both producers on the leader's full barriers; one multicast commit on everything the MMAs signal;
+        // one arrival per softmax warp of BOTH CTAs on what the issuers wait for (the peer's copies of those are never used)
+        const uint32_t bar0 = smem_base + L::kBarOff;
+        mbar_init(bar0 + 8 * L::kBarQFull, 2);
+        mbar_init(bar0 + 8 * L::kBarQEmpty, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar0 + 8 * (L::kBarKVFull + s), 2);
+            mbar_init(bar0 + 8 * (L::kBarKVEmpty + s), 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar0 + 8 * (L::kBarSFull + t), 1);
+            mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t), kPairWarpArrivals);
+            mbar_init(bar0 + 8 * (L::kBarPFull + 2 * t + 1), kPairWarpArrivals);
+            mbar_init(bar0 + 8 * (L::kBarOFull + t), 1);
+            mbar_init(bar0 + 8 * (L::kBarOFree + t), kPairWarpArrivals);
+            mbar_init(bar0 + 8 * (L::kBarSchedFull + t), 1);
+            // leader: its 2 issuers + 8 softmax warps, and the peer's 8 softmax warps + producer
+            mbar_init(bar0 + 8 * (L::kBarSchedEmpty + t), 2 + C::kSoftmaxWarps + C::kSoftmaxWarps + 1);
+            mbar_init(bar0 + 8 * (L::kBarSFree + t), kPairWarpArrivals);
+            mbar_init(bar0 + 8 * (L::kBarOHalf + t), 1);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        if (ST != 0) tma_prefetch_desc(&tmO);
+    }
+    __syncwarp();
+    cluster_sync_all();                                // every barrier of BOTH CTAs exists before anything signals across
+
+    uint32_t tmem_base = 0;
+    long long cta_t0 = 0;
+    if (warp == C::kLoadWarp) {
+        reg_dec<C::kOtherRegs>();
+        if (lane == 0) tmaPairLoaderThread<D, STAGES>(&tmQ, &tmK, &tmV, smem_base, p);
+    } else {
+        if (warp == C::kTmemWarp) {
+            tmem_alloc_pair(smem_base + L::kTmemPtrOff, kTmemCols);      // the same warp of both CTAs: 512 columns in each TMEM
+            tmem_relinquish_pair();
+        }
+        tc_fence_before();
+        named_bar_sync(9u, uint32_t(C::kNumThreads - 32));
+        tc_fence_after();
+        tmem_base = *tmem_ptr;
+        if (p.prof != nullptr && threadIdx.x == C::kNumThreads - 32) cta_t0 = clock64();
+
+        if (warp < C::kSoftmaxWarps) {
+            reg_inc<C::kSoftmaxRegs>();
+            softmaxWarpgroup<D, STAGES, DT, OVEC32, 0, ST, 0, 2>(smem_base, tmem_base, p, warp / 4, &tmO);
+        } else {
+            reg_dec<C::kOtherRegs>();
+            if (rank == 0) {
+                if (warp == C::kMmaWarp0) mmaPairIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 0);
+                else if (warp == C::kMmaWarp1) mmaPairIssuerWarp<D, STAGES, DT>(smem_base, tmem_base, p, 1);
+            }
+        }
+    }
+
+    // Nothing of either CTA may still be in flight towards the other's shared memory or TMEM when one of them exits.
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();
+    if (warp == C::kTmemWarp) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+    if (p.prof != nullptr && threadIdx.x == C::kNumThreads - 32) {
+        const unsigned long long dt = (unsigned long long)(clock64() - cta_t0);
+        atomicMax(p.prof + 30, dt);
+        atomicAdd(p.prof + 31, dt);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Exact-fp32 kernel (fp32 in, fp32 out, fp32 accumulate on the FMA pipe).  grid = (ceil(Nq/64), Hq, B),
 // 256 threads.  A 64-row query tile against 64-row key/value tiles staged in shared memory; each thread owns
 // a 4x4 patch of S and a 4 x (D/16) patch of O.  Used for fp32 I/O where TF32/bf16 tensor-core products would

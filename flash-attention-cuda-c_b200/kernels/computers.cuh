@@ -456,15 +456,152 @@ __device__ __forceinline__ void mmaTypeIssuerWarp(uint32_t smem_base, uint32_t t
 }
 
 // ------------------------------------------------------------------------------------------------
+// MMA issuers of a CTA pair (cta_group::2, d = 128, split by type like mmaTypeIssuerWarp).  They run in the LEADER CTA only:
+// one instruction multiplies the 256-row tile (128 rows of Q / P from each CTA) with a K / V tile of which each CTA's shared
+// memory holds half, and writes each CTA's 128 rows of S / O into its own TMEM.  Completion barriers that both CTAs wait on
+// (s_full, o_half, o_full, the ring's empty barriers, q_empty) get multicast commits; barriers the issuers wait on (q_full,
+// kv_full, s_free, p_full, o_free) live in the leader and collect arrivals from both CTAs — one per softmax WARP (8 in all)
+// instead of one per thread, so that the peer's arrivals are 4 remote operations per hand-off, not 128.
+// With an even number of ring slots K tiles always sit in even slots and V tiles in odd ones: each issuer only ever touches
+// its own slots.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairWarpArrivals = 2 * 4;      // softmax warps per query tile in the pair
+
+template <int D, int STAGES, int DT>
+__device__ __forceinline__ void mmaPairIssuerWarp(uint32_t smem_base, uint32_t tmem_base_in, const FwdParams& p, const int role) {
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);
+    using L = SmemLayout<D, STAGES, 2>;
+    static_assert(D == 128 && STAGES % 2 == 0, "pair kernel: d = 128, even ring");
+    constexpr uint32_t kFmt = (DT == kBF16) ? 1u : 0u;
+    constexpr uint32_t idesc_qk = umma_idesc(2 * kBlockM, kBlockN, kFmt, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc(2 * kBlockM, D, kFmt, 0, 1);
+    constexpr int kKHalfBytes = (kBlockN / 2) * 128;
+    const uint32_t bar0 = smem_base + L::kBarOff;
+    auto bar = [&](int i) { return bar0 + 8u * uint32_t(i); };
+    const uint64_t desc_k_major = umma_desc_sw128(0, 16, 1024);
+    const uint64_t desc_mn_major = umma_desc_sw128(0, kHalfBytes, 1024);
+    const uint32_t s_tmem = tmem_base + kTmemS;
+    auto slot_addr = [&](int it) { return smem_base + L::kKVOff + (it % STAGES) * L::kKVTileBytes; };
+    auto empty_bar = [&](int it) { return bar(L::kBarKVEmpty + it % STAGES); };
+    auto wait_full = [&](int it) {
+        mbar_wait(bar(L::kBarKVFull + it % STAGES), (it / STAGES) & 1);
+        tc_fence_after();
+    };
+
+    FA_T2_DECL;
+    int it0 = 0, kq = 0, sq = 0;
+    int st[2] = {0, 0}, ko[2] = {0, 0};
+    for (int k = 0;; ++k) {
+        WorkItem w;
+        const int item = fetch_item<D, STAGES, 2>(smem_base, k, w);
+        if (item < 0) break;
+        const int n = w.n_kv;
+        if (n <= 0) continue;
+        const int nts[2] = {w.n_tile0, w.n_tile1};
+        if (role == 0) {
+            mbar_wait(bar(L::kBarQFull), kq & 1);
+            ++kq;
+            for (int j = 0; j < n; ++j) {
+                wait_full(it0 + 2 * j);
+                const uint32_t k_smem = slot_addr(it0 + 2 * j);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int idx = (t == 0) ? sq + j - 1 : sq + j;
+                    if (idx >= 0) {
+                        mbar_wait(bar(L::kBarSFree + (1 - t)), idx & 1);
+                        tc_fence_after();
+                    }
+                    FA_T2(p.prof, 2, 70 + t);      // S buffer free for Q_t K_j^T
+                    if (elect_one_sync()) {
+                        if (j < nts[t]) {
+                            const uint64_t a0 = desc_k_major + ((smem_base + L::kQOff + t * L::kQTileBytes) >> 4);
+                            const uint64_t b0 = desc_k_major + (k_smem >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < D / 16; ++ks) {
+                                const uint32_t off_a = ((ks / 4) * kHalfBytes + (ks % 4) * 32) >> 4;
+                                const uint32_t off_b = ((ks / 4) * kKHalfBytes + (ks % 4) * 32) >> 4;
+                                umma_ss_pair(s_tmem, a0 + off_a, b0 + off_b, idesc_qk, ks > 0);
+                            }
+                            tc_commit_pair(bar(L::kBarSFull + t));
+                        } else {
+                            mbar_arrive_n(bar(L::kBarSFree + t), kPairWarpArrivals);      // virtual step: pass the buffer on
+                        }
+                    }
+                    __syncwarp();
+                    FA_T2(p.prof, 2, 6 + t);       // Q_t K_j^T issued
+                }
+                if (elect_one_sync()) {
+                    tc_commit_pair(empty_bar(it0 + 2 * j));
+                    if (j + 1 == n) tc_commit_pair(bar(L::kBarQEmpty));
+                }
+                __syncwarp();
+            }
+        } else {
+            for (int j = 0; j < n; ++j) {
+                wait_full(it0 + 2 * j + 1);
+                const uint64_t b0 = desc_mn_major + (slot_addr(it0 + 2 * j + 1) >> 4);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (j >= nts[t]) continue;
+                    const uint32_t ph = (st[t] + j) & 1;
+                    const uint32_t p_tmem = tmem_base + tmem_p_col(t);
+                    const uint32_t o_tmem = tmem_base + kTmemO0 + 128u * t;
+                    if (j == 0 && ko[t] > 0) mbar_wait(bar(L::kBarOFree + t), (ko[t] - 1) & 1);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        mbar_wait(bar(L::kBarPFull + 2 * t + half), ph);
+                        tc_fence_after();
+                        FA_T2(p.prof, 3, 74 + 2 * t + half);      // P half ready
+                        if (elect_one_sync()) {
+#pragma unroll
+                            for (int kk = 0; kk < kBlockN / 32; ++kk) {
+                                const int ks = half * (kBlockN / 32) + kk;
+                                umma_ts_pair(o_tmem, p_tmem + 8u * ks, b0 + ((ks * 2048) >> 4), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+                            }
+                            if (half == 1) tc_commit_pair(bar(L::kBarOFull + t));
+                            else if (kSplitOFull<D>) tc_commit_pair(bar(L::kBarOHalf + t));
+                        }
+                        __syncwarp();
+                        FA_T2(p.prof, 3, 78 + 2 * t + half);      // P V half issued
+                    }
+                }
+                if (elect_one_sync()) tc_commit_pair(empty_bar(it0 + 2 * j + 1));
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            st[t] += nts[t];
+            ko[t] += nts[t] > 0 ? 1 : 0;
+        }
+        sq += n;
+        it0 += 2 * n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Softmax warpgroup for query tile t (128 threads, one score row each), including the lazy O rescale and the
 // epilogue (O/l -> global, optional LSE).  Persistent: loops over the published work items; the epilogue of one item
 // overlaps the next item's first Q K^T.
 // ------------------------------------------------------------------------------------------------
-template <int D, int STAGES, int DT, bool OVEC32, int EMU, int ST, int HS>
+template <int D, int STAGES, int DT, bool OVEC32, int EMU, int ST, int HS, int CG = 1>
 __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tmem_base, const FwdParams& p, int t, const CUtensorMap* tmO) {
-    using L = SmemLayout<D, STAGES>;
+    using L = SmemLayout<D, STAGES, CG>;
+    static_assert(CG == 1 || (CG == 2 && HS == 0), "the pair kernel has no half items");
     uint32_t bar0 = smem_base + L::kBarOff;
     asm volatile("" : "+r"(bar0));     // keep in a register (see below)
+    // CTA pair: the barriers this warpgroup ARRIVES on live in the leader CTA (distance `to_lead` in the shared::cluster
+    // window; 0 in the leader itself) and take one arrival per warp
+    uint32_t to_lead = 0;
+    if constexpr (CG == 2) to_lead = mapa_shared(bar0, 0) - bar0;
+    auto sm_arrive = [&](uint32_t b) {
+        if constexpr (CG == 2) {
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(b + to_lead);
+        } else {
+            mbar_arrive(b);
+        }
+    };
     const uint32_t s_full = bar0 + 8u * (L::kBarSFull + t);
     const uint32_t p_full0 = bar0 + 8u * (L::kBarPFull + 2 * t);
     const uint32_t p_full1 = p_full0 + 8u;
@@ -490,7 +627,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
     for (int k = 0;; ++k) {
         if (k > 0 && warp_in_wg == 0) FA_T2(p.prof, 4 + t, 40 + t);      // the previous item's epilogue is done
         WorkItem w;
-        const int item = fetch_item<D, STAGES>(smem_base, k, w);
+        const int item = fetch_item<D, STAGES, CG>(smem_base, k, w);
         if (item < 0) break;
         const int n = w.n_tile(t);
         // a half item has no rows for query-tile slot 1: n == 0 (no barrier traffic) and its row numbers lie past every
@@ -498,7 +635,8 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
         // (Split-KV half item, HS = 1 kernels: both slots hold rows [q0, q0 + 128), slot t takes key tiles t, t+2, ... and slot 0
         // writes the merged result.  The launcher only plans such items when no step needs a mask — non-causal, Nk a multiple
         // of 128 — so the key loop below is untouched: the 216-register loop has no room for a second key-tile numbering.)
-        const int tile_row0 = (t * kBlockM < w.rows) ? w.q0 + t * kBlockM : kNoRow;
+        // (CTA pair: w.q0 is this CTA's own first row of the 512-row item, its tile t starts 256 t rows further)
+        const int tile_row0 = CG == 2 ? w.q0 + t * kPairTileRows : ((t * kBlockM < w.rows) ? w.q0 + t * kBlockM : kNoRow);
         const int row = tile_row0 + warp_in_wg * 32 + lane;
 
         float m_run = -INFINITY;   // max in use, in raw (unscaled) score units
@@ -534,7 +672,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             }
             tc_wait_ld();
             tc_fence_before();
-            mbar_arrive(s_free);         // the score row is in registers: the shared S buffer may be overwritten
+            sm_arrive(s_free);           // the score row is in registers: the shared S buffer may be overwritten
             if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 10 + t);
             FA_TRACE_EV(p.prof, k, t, 0, j, 1);
 #ifdef FA_PHASE_PROFILE
@@ -647,7 +785,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                 exp_quarter(2, pk);
                 tc_wait_st();                      // first half landed while quarter 2 was computed
                 tc_fence_before();
-                mbar_arrive(p_full0);              // MMA may start P V on keys 0..63
+                sm_arrive(p_full0);                // MMA may start P V on keys 0..63
                 FA_TRACE_EV(p.prof, k, t, 0, j, 3);
                 exp_quarter(3, pk + 16);
                 if (kSplitOFull<D> && j > 0) {
@@ -659,7 +797,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
             FA_PROF_MARK(3);             // exp2 / pack / tcgen05.st issue
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(p_full1);
+            sm_arrive(p_full1);
             if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 20 + t);
             FA_TRACE_EV(p.prof, k, t, 0, j, 4);
             FA_PROF_MARK(4);             // store drain + arrive
@@ -778,7 +916,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                     }
                     if (hf == D / kHalfCols - 1) {                    // O is out of TMEM: the next item's first P V may overwrite it
                         tc_fence_before();
-                        mbar_arrive(o_free);
+                        sm_arrive(o_free);
                     }
                     if (warp_in_wg == 0) FA_T2(p.prof, 4 + t, 36);      // half packed in registers
                     if (lane == 0) bulk_wait_group_read0();           // this warp's previous store has read the slice
@@ -826,7 +964,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(o_free);         // O columns may be overwritten by the next item's first P V
+                sm_arrive(o_free);           // O columns may be overwritten by the next item's first P V
             } else if (row_ok) {
 #pragma unroll
                 for (int i = 0; i < D / 8; ++i) st_global_v4(orow + 8 * i, 0u, 0u, 0u, 0u);
@@ -871,7 +1009,7 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(o_free);
+                sm_arrive(o_free);
             }
             if (row_ok && n > 0) p.acc_lse[acc_lin] = lse_new;
         }

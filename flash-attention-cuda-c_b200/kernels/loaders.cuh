@@ -118,10 +118,12 @@ struct FwdParams {
     unsigned long long* prof; // FA_PHASE_PROFILE builds only: per-phase cycle counters (see scripts/phase_profile.py)
 };
 
-template <int D, int STAGES>
+// CG = 2 (CTA-pair kernel, tcgen05 cta_group::2): a ring slot holds this CTA's HALF of a K tile (64 of the 128 keys, all d
+// columns) or of a V tile (all 128 keys, 64 of the d columns) — 16 KiB at d = 128; everything else is laid out as for CG = 1.
+template <int D, int STAGES, int CG = 1>
 struct SmemLayout {
     static constexpr int kQTileBytes = kBlockM * D * 2;
-    static constexpr int kKVTileBytes = kBlockN * D * 2;
+    static constexpr int kKVTileBytes = kBlockN * D * 2 / CG;
     static constexpr int kQOff = 0;
     static constexpr int kKVOff = kTilesPerCta * kQTileBytes;
     static constexpr int kBarOff = kKVOff + STAGES * kKVTileBytes;
@@ -230,19 +232,25 @@ __device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
 
 // Consumer side of the work-item hand-off (whole warp): returns the item index (-1 when the queue is drained) and the decoded
 // item the producer left in the mailbox slot (12 ints, three 128-bit shared-memory loads from a warp-uniform address).
-template <int D, int STAGES>
+template <int D, int STAGES, int CG = 1>
 __device__ __forceinline__ int fetch_item(uint32_t smem_base, int k, WorkItem& w) {
-    using L = SmemLayout<D, STAGES>;
+    using L = SmemLayout<D, STAGES, CG>;
     const uint32_t bar0 = smem_base + L::kBarOff;
     const int slot = k & 1;
-    mbar_wait(bar0 + 8 * (L::kBarSchedFull + slot), (k >> 1) & 1);
+    // CTA pair: the leader's producer writes both CTAs' mailboxes (remote stores + a remote arrive), and every consumer of
+    // either CTA hands the slot back on the LEADER's sched_empty barrier
+    if constexpr (CG == 2) mbar_wait_cluster(bar0 + 8 * (L::kBarSchedFull + slot), (k >> 1) & 1);
+    else mbar_wait(bar0 + 8 * (L::kBarSchedFull + slot), (k >> 1) & 1);
     const uint32_t a = smem_base + L::kSchedItemOff + L::kSchedSlotBytes * slot;
     int item, pad;
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(item), "=r"(w.b), "=r"(w.h), "=r"(w.h_kv) : "r"(a) : "memory");
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.q0), "=r"(w.rows), "=r"(w.split), "=r"(w.n_kv) : "r"(a + 16) : "memory");
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.n_steps), "=r"(w.n_tile0), "=r"(w.n_tile1), "=r"(pad) : "r"(a + 32) : "memory");
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(bar0 + 8 * (L::kBarSchedEmpty + slot));
+    if ((threadIdx.x & 31) == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(bar0 + 8 * (L::kBarSchedEmpty + slot), 0));
+        else mbar_arrive(bar0 + 8 * (L::kBarSchedEmpty + slot));
+    }
     return item;
 }
 
@@ -308,6 +316,17 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
                     const uint32_t parity = (it / STAGES) & 1;
                     const uint32_t full = bar0 + 8 * (L::kBarKVFull + s);
                     mbar_wait(bar0 + 8 * (L::kBarKVEmpty + s), parity ^ 1);
+#ifdef FA_EXP_NOKV
+                    // Energy experiment, WRONG RESULTS (scripts/README.md): once the ring has been filled, K/V tiles are not
+                    // loaded at all (1) or only their first 64 columns are (2) — the same instruction stream and MMA work with
+                    // none / half of the L2 -> shared-memory traffic.  Sizes what K/V multicast across a CTA pair could save.
+                    if (it >= STAGES) {
+                        if (FA_EXP_NOKV == 1) { mbar_arrive(full); continue; }
+                        mbar_expect_tx(full, L::kKVTileBytes / kHalves);
+                        tma_load_4d_hint(kv == 0 ? tmK : tmV, smem_base + L::kKVOff + s * L::kKVTileBytes, full, 0, j * kBlockN, w.h_kv, w.b, kEvictLast);
+                        continue;
+                    }
+#endif
                     mbar_expect_tx(full, L::kKVTileBytes);
                     FA_T2(p.prof, 1, 5);
                     const CUtensorMap* tm = kv == 0 ? tmK : tmV;
@@ -327,6 +346,133 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
     }
     // Tail: wait until the consumer has handed back the last fills, so that no tcgen05.commit arrive is still in
     // flight towards this CTA's shared memory when the CTA exits.
+    const int total = it;
+    for (int i = (total > STAGES ? total - STAGES : 0); i < total; ++i)
+        mbar_wait(bar0 + 8 * (L::kBarKVEmpty + i % STAGES), (i / STAGES) & 1);
+    if (kq > 0) mbar_wait(q_empty, (kq - 1) & 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel (d = 128): a work item is a 512-row query block of one (batch, head).  MMA tile t (t = 0, 1) of the pair is
+// the 256 rows [q0 + 256 t, q0 + 256 t + 256): the leader CTA owns the first 128 of them, the peer the last 128, each in its
+// own TMEM lanes.  Tile counts are those of the whole 256-row MMA tile (the leader's half of a causal tile's last key tile is
+// fully masked: its softmax sees -inf and writes P = 0).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairRows = 2 * kTilesPerCta * kBlockM;      // 512
+constexpr int kPairTileRows = 2 * kBlockM;                 // 256
+
+__device__ __forceinline__ WorkItem decode_pair_item(const FwdParams& p, int item) {
+    WorkItem w;
+    w.rows = kPairRows;
+    w.split = 0;
+    const int bh = fast_div(item, p.div_qblocks_mul, p.div_qblocks_shr);
+    const int r = item - bh * p.num_q_blocks;
+    const int qb = p.causal ? (p.num_q_blocks - 1 - r) : r;
+    w.b = fast_div(bh, p.div_hq_mul, p.div_hq_shr);
+    w.h = bh - w.b * p.Hq;
+    w.h_kv = fast_div(w.h, p.div_group_mul, p.div_group_shr);
+    w.q0 = qb * kPairRows;
+    const int n_all = (p.Nk + kBlockN - 1) / kBlockN;
+    w.n_kv = 0;
+#pragma unroll
+    for (int t = 0; t < kTilesPerCta; ++t) {
+        int n = n_all;
+        if (p.causal) {
+            const int last_col = w.q0 + (t + 1) * kPairTileRows - 1 + p.causal_off;
+            const int n_c = last_col < 0 ? 0 : last_col / kBlockN + 1;
+            n = n_c < n ? n_c : n;
+        }
+        if (w.q0 + t * kPairTileRows >= p.Nq) n = 0;
+        if (t == 0) w.n_tile0 = n; else w.n_tile1 = n;
+        w.n_kv = n > w.n_kv ? n : w.n_kv;
+    }
+    w.n_steps = w.n_kv;
+    return w;
+}
+
+// Producer thread of one CTA of a pair.  The leader's is also the pair's scheduler: it claims items, decodes them and writes
+// BOTH mailboxes (the peer's through distributed shared memory; q0 there is the peer's own first row).  Each producer loads
+// its own CTA's Q rows and its half of every K / V tile; all load completions land on the LEADER's full barriers (the MMA
+// issuers live there), slots come back through multicast tcgen05.commit arrivals on each CTA's own empty barriers.
+template <int D, int STAGES>
+__device__ __forceinline__ void tmaPairLoaderThread(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
+                                                    uint32_t smem_base, const FwdParams& p) {
+    using L = SmemLayout<D, STAGES, 2>;
+    static_assert(D == 128 && STAGES % 2 == 0, "pair kernel: d = 128, K in the even ring slots and V in the odd ones");
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t bar0 = smem_base + L::kBarOff;
+    const uint32_t lead0 = mapa_shared(bar0, 0);
+    const uint32_t q_full_l = lead0 + 8 * L::kBarQFull;
+    const uint32_t q_empty = bar0 + 8 * L::kBarQEmpty;
+    constexpr int kKHalfBytes = (kBlockN / 2) * 128;      // 64 keys x 64 columns
+
+    int it = 0, kq = 0;
+    int item = int(cluster_id_x());
+    for (int k = 0;; ++k) {
+        const int slot = k & 1;
+        WorkItem w{};
+        int pub;
+        if (rank == 0) {
+            mbar_wait_cluster(bar0 + 8 * (L::kBarSchedEmpty + slot), ((k >> 1) & 1) ^ 1);
+            pub = item < p.total_items ? item : -1;
+            if (pub >= 0) w = decode_pair_item(p, item);
+#pragma unroll
+            for (uint32_t c = 0; c < 2; ++c) {
+                const uint32_t a = mapa_shared(smem_base + L::kSchedItemOff + L::kSchedSlotBytes * slot, c);
+                st_shared_cluster_v4(a, pub, w.b, w.h, w.h_kv);
+                st_shared_cluster_v4(a + 16, w.q0 + int(c) * kBlockM, w.rows, 0, w.n_kv);
+                st_shared_cluster_v4(a + 32, w.n_steps, w.n_tile0, w.n_tile1, 0);
+                mbar_arrive_cluster_release(mapa_shared(bar0 + 8 * (L::kBarSchedFull + slot), c));
+            }
+        } else {
+            mbar_wait_cluster(bar0 + 8 * (L::kBarSchedFull + slot), (k >> 1) & 1);
+            const uint32_t a = smem_base + L::kSchedItemOff + L::kSchedSlotBytes * slot;
+            int pad;
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pub), "=r"(w.b), "=r"(w.h), "=r"(w.h_kv) : "r"(a) : "memory");
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.q0), "=r"(w.rows), "=r"(w.split), "=r"(w.n_kv) : "r"(a + 16) : "memory");
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.n_steps), "=r"(w.n_tile0), "=r"(w.n_tile1), "=r"(pad) : "r"(a + 32) : "memory");
+            mbar_arrive_cluster(lead0 + 8 * (L::kBarSchedEmpty + slot));
+        }
+        if (pub < 0) break;
+        if (w.n_kv > 0) {
+            mbar_wait(q_empty, (kq & 1) ^ 1);      // the previous item's last Q K^T has retired (multicast commit)
+            ++kq;
+            mbar_expect_tx_cluster(q_full_l, kTilesPerCta * L::kQTileBytes);
+#pragma unroll
+            for (int t = 0; t < kTilesPerCta; ++t)
+#pragma unroll
+                for (int hf = 0; hf < D / kHalfCols; ++hf)
+                    tma_load_4d_pair(tmQ, smem_base + L::kQOff + t * L::kQTileBytes + hf * kHalfBytes, q_full_l,
+                                     hf * kHalfCols, w.q0 + t * kPairTileRows, w.h, w.b, kEvictFirst);
+            for (int j = 0; j < w.n_kv; ++j) {
+                {   // this CTA's 64 keys of K_j, both 64-column halves
+                    const int s = it % STAGES;
+                    mbar_wait(bar0 + 8 * (L::kBarKVEmpty + s), ((it / STAGES) & 1) ^ 1);
+                    const uint32_t full_l = lead0 + 8 * (L::kBarKVFull + s);
+                    mbar_expect_tx_cluster(full_l, L::kKVTileBytes);
+#pragma unroll
+                    for (int hf = 0; hf < D / kHalfCols; ++hf)
+                        tma_load_4d_pair(tmK, smem_base + L::kKVOff + s * L::kKVTileBytes + hf * kKHalfBytes, full_l,
+                                         hf * kHalfCols, j * kBlockN + int(rank) * (kBlockN / 2), w.h_kv, w.b, kEvictLast);
+                    ++it;
+                }
+                {   // this CTA's 64 columns of V_j, all 128 keys
+                    const int s = it % STAGES;
+                    mbar_wait(bar0 + 8 * (L::kBarKVEmpty + s), ((it / STAGES) & 1) ^ 1);
+                    const uint32_t full_l = lead0 + 8 * (L::kBarKVFull + s);
+                    mbar_expect_tx_cluster(full_l, L::kKVTileBytes);
+                    tma_load_4d_pair(tmV, smem_base + L::kKVOff + s * L::kKVTileBytes, full_l,
+                                     int(rank) * kHalfCols, j * kBlockN, w.h_kv, w.b, kEvictLast);
+                    ++it;
+                }
+            }
+        }
+        if (rank == 0) {      // claim the pair's next item (same self-resetting counter as the 1-CTA kernel: one claim per cluster)
+            const int claimed = atomicAdd(p.sched_counter, 1);
+            if (claimed == p.total_items - 1) atomicExch(p.sched_counter, 0);
+            item = int(cluster_count_x()) + claimed;
+        }
+    }
     const int total = it;
     for (int i = (total > STAGES ? total - STAGES : 0); i < total; ++i)
         mbar_wait(bar0 + 8 * (L::kBarKVEmpty + i % STAGES), (i / STAGES) & 1);

@@ -278,6 +278,101 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs of a pair run on the two SMs of one TPC.  One MMA instruction,
+// issued by the even ("leader") CTA, multiplies a 256-row A (128 rows from each CTA's own shared memory / TMEM) with a B whose N
+// dimension is split over the two CTAs' shared memories, and leaves each CTA its own 128 rows of D in its own TMEM — every CTA
+// loads and reads only HALF of each K / V tile.  Shared-window addresses of a CTA are valid shared::cluster addresses of its
+// own memory; mapa gives the address of the same offset in another CTA of the cluster.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+// arrive / expect_tx on an mbarrier of ANY CTA of the cluster (address from mapa_shared).  Default semantics (release at CTA
+// scope) for the TMEM hand-offs, whose ordering comes from the tcgen05 fences: a cluster-scope release costs the arriving
+// warp several hundred cycles each time (measured: three of them per step made the softmax 1.5x slower).  The cluster-scope
+// form is for the one hand-off that publishes ordinary shared-memory DATA to the other CTA (the work-item mailbox).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t caddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t caddr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(caddr), "r"(bytes) : "memory");
+}
+// parity wait on a LOCAL mbarrier whose arrivals come from the other CTA (acquire at cluster scope); same hang guard
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > FA_HANG_GUARD_CYCLES) mbar_hang_report(bar, parity);
+    }
+}
+__device__ __forceinline__ void st_shared_cluster_v4(uint32_t caddr, int a, int b, int c, int d) {
+    asm volatile("st.shared::cluster.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// TMA load issued by either CTA of a pair: data into the issuing CTA's shared memory, completion bytes onto the mbarrier at
+// `bar_caddr` (a shared::cluster address: the LEADER's barrier, whichever CTA issues)
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, uint32_t dst_smem, uint32_t bar_caddr,
+                                                 int c0, int c1, int c2, int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_caddr), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+          "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {   // one whole warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive (count 1) on the mbarrier at the same offset in every CTA of `mask` once all MMAs issued so far by this thread retire
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask = 3) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // tcgen05.ld / tcgen05.st, shape 32x32b: thread i of the warp <-> TMEM lane (lane_base + i),
 // N consecutive 32-bit columns per thread.
 // ------------------------------------------------------------------------------------------

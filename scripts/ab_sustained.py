@@ -19,7 +19,7 @@ for nm in names:     # "<lib>@sw,emu" forces a compiled kernel variant of that l
     fa_b200._lib = None
     fa_b200.LIB_PATH = os.path.join(ROOT, "variants", f"libfa_v_{base}.so") if base != "shipped" else os.path.join(ROOT, "flash-attention-cuda-c_b200", "libfa_b200.so")
     libs[nm] = fa_b200.lib()
-    force[nm] = tuple(int(x) for x in (fv + ",0").split(",")[:3]) if fv else None
+    force[nm] = tuple(int(x) for x in (fv + ",0,0").split(",")[:4]) if fv else None
 for si in sel:
     B, Hq, Hkv, N, d, causal, dt = SHAPES[si]
     t = {"bf16": torch.bfloat16, "fp16": torch.float16}[dt]
@@ -31,7 +31,10 @@ for si in sel:
     for r in range(rounds):
         for nm in names[r % len(names):] + names[:r % len(names)]:
             fa_b200._lib = libs[nm]
-            try: libs[nm].fa_debug_force_variant(*(force[nm] or (0, 0, 0)))
+            try:
+                fv4 = force[nm] or (0, 0, 0, 0)
+                libs[nm].fa_debug_force_variant(*fv4[:3])
+                if hasattr(libs[nm], "fa_debug_force_cta_group"): libs[nm].fa_debug_force_cta_group(fv4[3])
             except (AttributeError, TypeError): pass
             for _ in range(warm): fa_b200.attention_forward(q, k, v, causal=causal, out=o)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

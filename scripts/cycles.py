@@ -21,7 +21,7 @@ for n in names:      # "name" = variants/libfa_v_<name>.so, "shipped" = the in-t
     fa_b200.LIB_PATH = os.path.join(ROOT, "variants", f"libfa_v_{base}.so") if base != "shipped" else os.path.join(ROOT, "flash-attention-cuda-c_b200", "libfa_b200.so")
     libs[n] = fa_b200.lib()
     libs[n].fa_debug_set_profile_buffer.argtypes = [ctypes.c_void_p]
-    force[n] = tuple(int(x) for x in (fv + ",0").split(",")[:3]) if fv else None
+    force[n] = tuple(int(x) for x in (fv + ",0,0").split(",")[:4]) if fv else None
 prof = torch.zeros(32, dtype=torch.int64, device="cuda")
 for si in sel:
     B, Hq, Hkv, N, d, causal, dt = SHAPES[si]
@@ -36,7 +36,10 @@ for si in sel:
         for n in names:
             fa_b200._lib = libs[n]
             if force[n] is not None or hasattr(libs[n], "fa_debug_force_variant"):
-                try: libs[n].fa_debug_force_variant(*(force[n] or (0, 0, 0)))
+                try:
+                    fv4 = force[n] or (0, 0, 0, 0)
+                    libs[n].fa_debug_force_variant(*fv4[:3])
+                    if hasattr(libs[n], "fa_debug_force_cta_group"): libs[n].fa_debug_force_cta_group(fv4[3])
                 except (AttributeError, TypeError): pass
             libs[n].fa_debug_set_profile_buffer(None)
             fa_b200.attention_forward(q, k, v, causal=causal, out=o)

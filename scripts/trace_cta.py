@@ -19,7 +19,9 @@ L.fa_debug_set_profile_buffer(None)
 p = prof.cpu().tolist()
 NAMES = {1: "kernel entry", 2: "set-up done", 3: "item published", 4: "Q loads issued", 5: "K/V tile issued", 6: "QK issued slot0", 7: "QK issued slot1",
          10: "S taken slot0", 11: "S taken slot1", 20: "P delivered slot0", 21: "P delivered slot1", 30: "epilogue begins slot0", 31: "epilogue begins slot1",
-         35: "last PV retired (epilogue)", 36: "O chunk in registers", 37: "staging piece free", 38: "piece written", 39: "piece visible to TMA", 60: "producer running", 61: "item decoded", 62: "Q buffers free", 40: "epilogue done slot0", 41: "epilogue done slot1", 50: "CTA done"}
+         35: "last PV retired (epilogue)", 36: "O chunk in registers", 37: "staging piece free", 38: "piece written", 39: "piece visible to TMA", 60: "producer running", 61: "item decoded", 62: "Q buffers free", 40: "epilogue done slot0", 41: "epilogue done slot1", 50: "CTA done",
+         70: "S buffer free for QK slot0", 71: "S buffer free for QK slot1", 74: "P half0 ready slot0", 75: "P half1 ready slot0", 76: "P half0 ready slot1", 77: "P half1 ready slot1",
+         78: "PV half0 issued slot0", 79: "PV half1 issued slot0", 80: "PV half0 issued slot1", 81: "PV half1 issued slot1"}
 ev = sorted(((x & 0xffffffffffff), (x >> 48) & 0xffff) for x in p[64:] if x)
 t0 = ev[0][0]
 for c, code in ev: print(f"{c - t0:8d}  {NAMES.get(code, code)}")
