@@ -461,6 +461,11 @@ def run_ours(args, wl, wl_name):
     if rank == 0:
         burst, sustained, hbm, how = peaks()
         k_ms = sum(kernel_ms) / len(kernel_ms)          # this rank's mean per-step time from the per-step event pairs
+        kernel_name = "fa::fwdFp32Kernel"
+        if dtype != "fp32":      # what the launcher's tile table picks for this workload
+            tc = fa_b200.choose_tile(d, {"bf16": fa_b200.FA_DTYPE_BF16, "fp16": fa_b200.FA_DTYPE_F16}[dtype], causal, N, N)
+            kernel_name = "fa::fwdSm100PairKernel (CTA pairs, cta_group::2)" if tc["cta_group"] == 2 else "fa::fwdSm100Kernel"
+            kernel_name += f" [softmax warps {tc['softmax_warps']}, staged epilogue {tc['staged_epilogue']}, ring slots {tc['stages']}]"
         per_gpu = F / (k_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -474,7 +479,7 @@ def run_ours(args, wl, wl_name):
                     "frac_of_nominal_2250": per_gpu / 2250.0,
                     "traffic": traffic, "algorithmic_bytes": alg_bytes, "algorithmic_flops": F,
                     "hbm_gbs_achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm,
-                    "kernel": "fa::fwdSm100Kernel", "kernel_ms": k_ms}
+                    "kernel": kernel_name, "kernel_ms": k_ms}
         if sustained_rec is not None:
             sustained_rec["peak_sustained"] = sustained
             sustained_rec["frac_of_sustained_peak"] = sustained_rec["per_gpu"] / sustained

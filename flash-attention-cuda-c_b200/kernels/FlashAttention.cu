@@ -10,6 +10,7 @@
 
 #include <cuda_fp16.h>
 #include <atomic>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -177,22 +178,24 @@ int* next_counter(cudaStream_t st, int* sm_count_out) {
 // ---- measured tile table -----------------------------------------------------------------------------
 // Stands where the reference's calculateSizeBlockQ / calculateSizeBlockKV sketch register- and L2-driven formulas and then
 // return 64 (reference: helpers.hpp:8-30): per (head dim, causal, key-length bucket) the kernel variant that measured
-// fastest on B200 (scripts/tile_sweep.py -> profiles/r2_tile_sweep.jsonl: 28 shapes x the three compiled variants, six
-// interleaved rounds of 250 ms of back-to-back launches each under the power cap; `tflops` is that run's figure).  fp16 takes the bf16 rows (same cycle counts).
+// fastest on B200 (scripts/tile_sweep.py -> profiles/r2_tile_sweep.jsonl: 28 shapes x the compiled variants, four
+// interleaved rounds of 200 ms of back-to-back launches each under the power cap; `tflops` is that run's figure).  fp16 takes the bf16 rows (same cycle counts).
 // Tile geometry is the same in every row — 256 query rows per work item (2 x 128-row MMA tiles ping-ponged through the tensor
-// pipe), 128 key rows per pipeline stage, the whole TMEM and shared memory of an SM, 1-CTA MMAs — because the sweeps that
-// varied it lost: 64-key steps run the SS MMA at half rate, and no 2-CTA variant is built.  What varies is the softmax
-// layout (8 warps x one row per thread / 16 warps x 16-lane fragments), the share of exponentials moved to the FMA pipe,
-// and how O leaves the SM (row-per-lane st.global, or staged per warp through shared memory + TMA stores, which at d = 128
-// costs the K/V ring its fifth slot and still wins).
+// pipe), 128 key rows per pipeline stage, the whole TMEM and shared memory of an SM — because the sweeps that varied it
+// lost: 64-key steps run the SS MMA at half rate.  What varies is the softmax layout (8 warps x one row per thread / 16 warps
+// x 16-lane fragments), the share of exponentials moved to the FMA pipe, how O leaves the SM (row-per-lane st.global, or
+// staged per warp through shared memory + TMA stores, which at d = 128 costs the 1-CTA K/V ring its fifth slot and still
+// wins), and whether the MMAs are 1-CTA or CTA-pair (cta_group 2: fwdSm100PairKernel — two CTAs on the SMs of one TPC share
+// every K/V tile half and half, 512 query rows per pair item, six 16 KiB ring slots; block_q stays the rows per CTA).
 const fa_tile_choice_t kTileTable[] = {
     //  d  causal n_min  block_q block_kv stages sm_warps emu staged issuer cta  tflops (first bucket of the row: N = n_min, or 512)
-    {128, 0,     0,  256, 128, 4,  8, 0, 1, 1, 1,  867.3f},   // staged epilogue at every length: +5.4 % at N = 512, +2.9 % at 2K, +0.9 % at 8K, +0.6 % at 32K
-    {128, 1,     0,  256, 128, 4,  8, 0, 1, 1, 1,  527.6f},   // causal: +1.2 % at 512, +2.0 % at 1K, +1.3 % at 2K, +0.3 % at 8K (the fourth ring slot is enough)
-    { 64, 0,     0,  256, 128, 8,  8, 0, 1, 0, 1,  642.5f},   // N = 512: +5.7 %, N = 1024 (BASELINE configs[1]): +3.0 %, 2K: +1.6 %
-    { 64, 0,  4096,  256, 128, 8, 16, 1, 0, 0, 1,  807.8f},   // MUFU-bound: 16 softmax warps + 1/8 of the exponentials on the FMA pipe, +1.4 .. +2.1 %
-    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 0, 1,  389.2f},   // staged: -1.5 % at 512, equal from 1K to 4K
-    { 64, 1,  8192,  256, 128, 8, 16, 1, 0, 0, 1,  783.7f},   // +0.8 % at 8K, +1.3 % at 16K, +2.0 % at 32K
+    {128, 0,     0,  256, 128, 6,  8, 0, 1, 1, 2,  910.6f},   // CTA pairs at every length: +3.8 % over the staged 1-CTA kernel at N = 512, +4.0 % at 2K, +4.2 % at 8K, +3.0 % at 32K
+    {128, 1,     0,  256, 128, 4,  8, 0, 1, 1, 1,  537.4f},   // causal below 8K: 512-row pair items are too coarse (-7 % at 512, -4 % at 2K, -0.5 % at 4K)
+    {128, 1,  8192,  256, 128, 6,  8, 0, 1, 1, 2, 1196.5f},   // +1.7 % at 8K, +3.2 % at 16K, +3.5 % at 32K
+    { 64, 0,     0,  256, 128, 8,  8, 0, 1, 0, 1,  652.2f},   // staged epilogue: +5.7 % at N = 512, +3.4 % at 1024 (BASELINE configs[1]), +1.9 % at 2K
+    { 64, 0,  4096,  256, 128, 8, 16, 1, 0, 0, 1,  816.6f},   // MUFU-bound: 16 softmax warps + 1/8 of the exponentials on the FMA pipe, +0.4 % at 4K .. +2.0 % at 32K
+    { 64, 1,     0,  256, 128, 8,  8, 0, 0, 0, 1,  396.9f},   // staged: -1.3 % at 512, equal from 1K to 4K
+    { 64, 1,  8192,  256, 128, 8, 16, 1, 0, 0, 1,  790.0f},   // +0.6 % at 8K, +1.7 % at 16K, +2.2 % at 32K
 };
 constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
 std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_force_cg{0}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
@@ -325,6 +328,7 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMa
         e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
         if (e != cudaSuccess || n < 1) return fail(FA_ERR_CUDA, "cudaOccupancyMaxActiveClusters(pair kernel) -> %s (%d)", cudaGetErrorString(e), n);
         max_pairs_dev[dev & 63].store(n);
+        if (getenv("FA_DEBUG_PAIRS")) fprintf(stderr, "fa_b200: device %d holds %d CTA pairs at once\n", dev, n);
         dev_mask.fetch_or(1ull << dev);
     }
     const int num_q_blocks = (p.Nq + fa::kPairRows - 1) / fa::kPairRows;

@@ -131,13 +131,14 @@ int fa_block_kv(int d, int dtype);
  * B200.  A row applies to Nk >= n_min; of the matching rows the one with the largest n_min wins.  The launcher uses it. */
 typedef struct {
     int d, causal, n_min;      /* key */
-    int block_q, block_kv;     /* query rows per work item (2 MMA tiles of 128), key rows per pipeline stage */
-    int stages;                /* K/V ring slots in shared memory */
+    int block_q, block_kv;     /* query rows per CTA and work item (2 MMA tiles of 128), key rows per pipeline stage */
+    int stages;                /* K/V ring slots in shared memory (cta_group 2: slots of half a tile) */
     int softmax_warps;         /* 8: one score row per thread; 16: 16-lane TMEM fragments, 4 softmax warps per SM sub-partition */
     int emu_pairs_per_8;       /* of every 8 score pairs, this many take exp2 on the FMA pipe instead of MUFU.EX2 */
     int staged_epilogue;       /* 1: O leaves through shared memory and TMA stores (d = 128: `stages` is 4 then), 0: row-per-lane st.global */
     int issuer_by_type;        /* MMA issuer warps split by type (all QK^T / all PV) instead of by query tile */
-    int cta_group;             /* 1: single-CTA tcgen05.mma (no 2-CTA variant is built) */
+    int cta_group;             /* 1: single-CTA tcgen05.mma; 2: CTA pairs (clusters of 2, tcgen05 cta_group::2, d = 128): the two CTAs of a
+                                * pair share each K/V tile half and half and work on 2 x block_q query rows per item */
     float tflops;              /* measured for the bucket's representative shape (profiles/r2_tile_sweep.jsonl); 0 = not measured */
 } fa_tile_choice_t;
 int fa_tile_table(const fa_tile_choice_t** rows);                                              /* returns the row count */

@@ -8,5 +8,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "launch list rc=$?"; tail -4 gpurun_out/r2_launches.csv | cut -c1-300
 echo "== ncu full"
 $CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fwdSm100Kernel -s 3 -c 2 -f -o gpurun_out/r2_prof $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fwdSm100 -s 3 -c 2 -f -o gpurun_out/r2_prof $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full rc=$?"; tail -3 gpurun_out/ncu_full.log

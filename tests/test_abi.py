@@ -52,11 +52,15 @@ def test_host_helpers(L):
     rows = fa_b200.tile_table()
     assert {(r["d"], r["causal"]) for r in rows if r["n_min"] == 0} == {(128, 0), (128, 1), (64, 0), (64, 1)}
     for r in rows:
-        assert r["block_q"] == 256 and r["block_kv"] == 128 and r["softmax_warps"] in (8, 16) and r["cta_group"] == 1
+        assert r["block_q"] == 256 and r["block_kv"] == 128 and r["softmax_warps"] in (8, 16) and r["cta_group"] in (1, 2)
         assert r["issuer_by_type"] == (1 if r["d"] == 128 else 0) and r["tflops"] > 0
-        # compiled variants: (8 warps, direct), (8 warps, staged TMA-store epilogue: 4 ring slots at d = 128), (16 warps + FMA-pipe exp2)
+        # compiled variants: (8 warps, direct), (8 warps, staged TMA-store epilogue: 4 ring slots at d = 128), (16 warps + FMA-pipe exp2);
+        # the CTA-pair kernel (cta_group 2: d = 128, 8 warps, six half-tile ring slots) exists with either epilogue
         assert (r["softmax_warps"], r["emu_pairs_per_8"], r["staged_epilogue"]) in ((8, 0, 0), (8, 0, 1), (16, 1, 0))
-        assert r["stages"] == (8 if r["d"] == 64 else (4 if r["staged_epilogue"] else 5))
+        if r["cta_group"] == 2:
+            assert r["d"] == 128 and r["softmax_warps"] == 8 and r["stages"] == 6
+        else:
+            assert r["stages"] == (8 if r["d"] == 64 else (4 if r["staged_epilogue"] else 5))
     for d in (64, 128):
         for causal in (0, 1):
             for nk in (100, 1024, 4096, 100000):

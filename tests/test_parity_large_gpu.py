@@ -139,6 +139,62 @@ def test_many_work_items_carry_mode(d):
     assert np.abs(acc_o[b:b + 1, h:h + 1].cpu().numpy() - ref).max() <= TOL16
 
 
+# ---- the CTA-pair kernel (clusters of 2, tcgen05 cta_group::2) and its 1-CTA counterpart, each forced --------------------
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("staged", [0, 1])
+@pytest.mark.parametrize("causal,nq,nk", [(False, 1000, 1000), (True, 1000, 1000), (True, 700, 1300), (False, 513, 384), (True, 2100, 2100)])
+def test_cta_pair_and_single_kernels_forced(cta_group, staged, causal, nq, nk):
+    # The tile table picks the pair kernel for d = 128 non-causal and for causal Nk >= 8K; here both kernels run every shape:
+    # 512-row pair items with a ragged last item (rows past Nq in the peer CTA only: nq = 513), fully masked leader half
+    # tiles on every causal diagonal, Nq != Nk, GQA, more items than pairs (6 x 12 x 3..5 items on 74 pairs), LSE.
+    B, Hq, Hkv, d = 6, 12, 4, 128
+    dtype = torch.float16 if (nq + staged) % 2 else torch.bfloat16
+    q, k, v = _rand((B, Hq, nq, d), dtype, 31), _rand((B, Hkv, nk, d), dtype, 32), _rand((B, Hkv, nk, d), dtype, 33)
+    try:
+        fa_b200.force_variant(8, 0, staged, cta_group)
+        out, lse = fa_b200.attention_forward(q, k, v, causal=causal, return_lse=True)
+        torch.cuda.synchronize()
+    finally:
+        fa_b200.force_variant(0, 0, 0, 0)
+    o_t, lse_t = _torch_ref(q, k, v, causal)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - o_t).abs().max().item() <= TOL16
+    fin = torch.isfinite(lse_t)
+    assert (torch.isfinite(lse) == fin).all() and (lse[fin] - lse_t[fin]).abs().max().item() <= 2e-3
+    _oracle_slices(q, k, v, out, lse, causal, [(0, 0), (B - 1, Hq - 1)])
+
+
+def test_cta_pair_kernel_carry_window():
+    # ring-step form on the pair kernel: two key ranges folded into a row window of a larger fp32 accumulator
+    B, Hq, Hkv, nq, nk, d = 3, 8, 8, 1024, 1536, 128
+    q, k, v = _rand((B, Hq, nq, d), torch.bfloat16, 41), _rand((B, Hkv, nk, d), torch.bfloat16, 42), _rand((B, Hkv, nk, d), torch.bfloat16, 43)
+    rows, off = nq + 512, 256
+    acc_o = torch.zeros(B, Hq, rows, d, device="cuda")
+    acc_l = torch.full((B, Hq, rows), float("-inf"), device="cuda")
+    try:
+        fa_b200.force_variant(8, 0, 0, 2)
+        fa_b200.attention_forward_carry(q, k[:, :, :512], v[:, :, :512], acc_o, acc_l, causal=False, row_offset=off)
+        fa_b200.attention_forward_carry(q, k[:, :, 512:], v[:, :, 512:], acc_o, acc_l, causal=True, row_offset=off)
+        torch.cuda.synchronize()
+    finally:
+        fa_b200.force_variant(0, 0, 0, 0)
+    o1, l1 = _torch_ref(q, k[:, :, :512], v[:, :, :512], False)
+    o2, l2 = _torch_ref(q, k[:, :, 512:], v[:, :, 512:], True)
+    l_ref = torch.logaddexp(l1, l2)
+    o_ref = o1 * torch.exp(l1 - l_ref).nan_to_num(0.0)[..., None] + o2 * torch.exp(l2 - l_ref).nan_to_num(0.0)[..., None]
+    assert (acc_o[:, :, off:off + nq] - o_ref).abs().max().item() <= TOL16
+    assert (acc_l[:, :, off:off + nq] - l_ref).abs().max().item() <= 2e-3
+    assert (acc_o[:, :, :off] == 0).all() and (acc_o[:, :, off + nq:] == 0).all()      # rows outside the window untouched
+    b, h = B - 1, Hq - 1
+    qq, kk, vv = (t.float().cpu().numpy() for t in (q[b:b + 1, h:h + 1], k[b:b + 1, h:h + 1], v[b:b + 1, h:h + 1]))
+    a1, m1 = oracle.attention_fwd(qq, kk[:, :, :512], vv[:, :, :512], return_lse=True)
+    a2, m2 = oracle.attention_fwd(qq, kk[:, :, 512:], vv[:, :, 512:], causal=True, return_lse=True)
+    mm = np.logaddexp(m1, m2)
+    with np.errstate(invalid="ignore"):
+        ref = a1 * np.nan_to_num(np.exp(m1 - mm))[..., None] + a2 * np.nan_to_num(np.exp(m2 - mm))[..., None]
+    assert np.abs(acc_o[b:b + 1, h:h + 1, off:off + nq].cpu().numpy() - ref).max() <= TOL16
+
+
 @pytest.mark.parametrize("nk", [128, 384, 1024])           # 1 key tile (slot 1 gets none), odd and even tile counts
 @pytest.mark.parametrize("d,dtype", [(128, torch.bfloat16), (64, torch.float16)])
 def test_half_item_tail_split_kv(d, dtype, nk):
