@@ -338,7 +338,7 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMa
     int* counter = next_counter(st, &sm_count);
     if (!counter) return fail(FA_ERR_CUDA, "work-item counter allocation failed");
     int max_pairs = max_pairs_dev[dev & 63].load();
-    const int by_reserve = (sm_count - g_sm_reserve.load()) / 2;
+    const int by_reserve = (sm_count - g_sm_reserve.load()) / 2;      // fa_set_sm_reserve: SMs left free (small reserves only, see fwd_impl)
     if (by_reserve < max_pairs) max_pairs = by_reserve;
     if (max_pairs < 1) max_pairs = 1;
     p.num_q_blocks = num_q_blocks;
@@ -458,6 +458,11 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     const bool bf = dtype == FA_DTYPE_BF16;
     int cg = tc ? tc->cta_group : 1;
     if (g_force_cg.load()) cg = g_force_cg.load();
+    // A reserve of 8 or more SMs means a communication KERNEL runs beside the attention launch (NCCL send/recv in the ring's
+    // p2p transport).  Its CTAs land on SMs of different TPCs, a TPC with one SM taken cannot hold a pair, and the pairs that
+    // do not fit queue behind the communication kernel: measured on 2 GPUs, 15.4-16.1 ms per ring pass with pairs against
+    // 14.7 ms with 1-CTA kernels.  So the pair kernel is only used with small reserves (copy-engine transports).
+    if (g_sm_reserve.load() >= 8 && !g_force_cg.load()) cg = 1;
     if (cg == 2 && d == 128 && sw == 8) {
         // CTA pairs: each CTA loads 64 of a K tile's 128 keys (its own tensor map: 64-row boxes) and 64 of a V tile's columns
         CUtensorMap tk64;
