@@ -44,12 +44,12 @@ void print_tile_table() {
     const fa_tile_choice_t* rows = nullptr;
     const int n = fa_tile_table(&rows);
     printf("tile table (%d rows; a row applies to Nk >= n_min, the largest matching n_min wins):\n", n);
-    printf("  %4s %6s %7s | %7s %8s %6s %13s %9s %14s %9s | %s\n", "d", "causal", "n_min", "block_q", "block_kv", "stages",
-           "softmax_warps", "exp2_emu", "issuer_by_type", "cta_group", "measured TFLOP/s");
+    printf("  %4s %6s %7s | %7s %8s %6s %13s %9s %6s %14s %9s | %s\n", "d", "causal", "n_min", "block_q", "block_kv", "stages",
+           "softmax_warps", "exp2_emu", "staged", "issuer_by_type", "cta_group", "measured TFLOP/s");
     for (int i = 0; i < n; ++i)
-        printf("  %4d %6d %7d | %7d %8d %6d %13d %7d/8 %14d %9d | %.0f\n", rows[i].d, rows[i].causal, rows[i].n_min, rows[i].block_q,
-               rows[i].block_kv, rows[i].stages, rows[i].softmax_warps, rows[i].emu_pairs_per_8, rows[i].issuer_by_type, rows[i].cta_group,
-               rows[i].tflops);
+        printf("  %4d %6d %7d | %7d %8d %6d %13d %7d/8 %6d %14d %9d | %.0f\n", rows[i].d, rows[i].causal, rows[i].n_min, rows[i].block_q,
+               rows[i].block_kv, rows[i].stages, rows[i].softmax_warps, rows[i].emu_pairs_per_8, rows[i].staged_epilogue, rows[i].issuer_by_type,
+               rows[i].cta_group, rows[i].tflops);
 }
 
 namespace {
@@ -164,8 +164,9 @@ int main(int argc, char** argv) {
     const fa_tile_choice_t tile = chooseTile(o.d, o.dtype, o.causal != 0, o.N, o.N);
     const int bq = tile.block_q, bkv = tile.block_kv;
     (void)prop;
-    printf("%s | tiles: %d query rows / work item, %d kv rows / stage x %d stages, %d softmax warps, exp2 on the FMA pipe %d/8, %d work items per (batch, head)\n",
-           fa_version(), bq, bkv, tile.stages, tile.softmax_warps, tile.emu_pairs_per_8, getNumCta(o.N, bq));
+    printf("%s | tiles: %d query rows / work item (%d CTA%s per MMA), %d kv rows / stage x %d stages, %d softmax warps, exp2 on the FMA pipe %d/8, %d work items per (batch, head)\n",
+           fa_version(), bq * tile.cta_group, tile.cta_group, tile.cta_group > 1 ? "s" : "", bkv, tile.stages, tile.softmax_warps, tile.emu_pairs_per_8,
+           getNumCta(o.N, bq * tile.cta_group));
 
     // (batch, kv-head) units -> contiguous slices, one per GPU, no communication
     const long long units = (long long)o.B * o.Hkv;
