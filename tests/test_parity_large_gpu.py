@@ -164,6 +164,39 @@ def test_cta_pair_and_single_kernels_forced(cta_group, staged, causal, nq, nk):
     _oracle_slices(q, k, v, out, lse, causal, [(0, 0), (B - 1, Hq - 1)])
 
 
+def test_cta_pair_kernel_bit_identical_to_single_kernel_on_random_shapes():
+    # Both kernels do the same per-row arithmetic in the same order (half items off: a split-KV tail sums in another order), so
+    # O and LSE must agree to the bit on any shape — 120 random ones: B, GQA group, ragged Nq, Nq != Nk, causal, dtype, epilogue.
+    import ctypes
+    import random
+    rng = random.Random(7)
+    L = fa_b200.lib()
+    L.fa_debug_half_items.argtypes = [ctypes.c_int]
+    try:
+        L.fa_debug_half_items(0)
+        for i in range(120):
+            g = rng.choice([1, 1, 2, 4, 8])
+            Hkv = rng.choice([1, 2, 3]); Hq = Hkv * g
+            B = rng.choice([1, 2, 3])
+            Nq = rng.choice([1, 17, 128, 129, 255, 256, 257, 511, 512, 513, 700, 1000, 1024, 1500, 2048, rng.randrange(1, 3000)])
+            Nk = Nq if rng.random() < 0.5 else rng.choice([1, 64, 127, 128, 129, 300, 512, 1000, 2048, rng.randrange(1, 4000)])
+            causal = rng.random() < 0.6
+            dt = rng.choice([torch.bfloat16, torch.float16])
+            stg = rng.choice([0, 1])
+            q, k, v = _rand((B, Hq, Nq, 128), dt, 3 * i), _rand((B, Hkv, Nk, 128), dt, 3 * i + 1), _rand((B, Hkv, Nk, 128), dt, 3 * i + 2)
+            fa_b200.force_variant(8, 0, stg, 1)
+            o1, l1 = fa_b200.attention_forward(q, k, v, causal=causal, return_lse=True)
+            fa_b200.force_variant(8, 0, stg, 2)
+            o2, l2 = fa_b200.attention_forward(q, k, v, causal=causal, return_lse=True)
+            torch.cuda.synchronize()
+            what = f"shape {i}: B{B} Hq{Hq} Hkv{Hkv} Nq{Nq} Nk{Nk} causal={causal} {dt} staged={stg}"
+            assert torch.equal(o1.view(torch.int16), o2.view(torch.int16)), what
+            assert torch.equal(l1.view(torch.int32), l2.view(torch.int32)), what
+    finally:
+        fa_b200.force_variant(0, 0, 0, 0)
+        L.fa_debug_half_items(1)
+
+
 def test_cta_pair_kernel_carry_window():
     # ring-step form on the pair kernel: two key ranges folded into a row window of a larger fp32 accumulator
     B, Hq, Hkv, nq, nk, d = 3, 8, 8, 1024, 1536, 128
