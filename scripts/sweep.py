@@ -48,5 +48,5 @@ for (B, Hq, Hkv, N, d, causal, dt) in SHAPES:
     print(json.dumps({"B": B, "Hq": Hq, "Hkv": Hkv, "N": N, "d": d, "causal": causal, "dtype": dt,
                       "steady_ms": round(st, 4), "steady_tflops": round(F / st / 1e9, 1), "steady_gbs": round(by / st / 1e6, 1),
                       "isolated_ms_median": round(iso, 4), "isolated_tflops": round(F / iso / 1e9, 1),
-                      "variant": [tile["softmax_warps"], tile["emu_pairs_per_8"], tile["staged_epilogue"]]}), flush=True)
+                      "variant": [tile["softmax_warps"], tile["emu_pairs_per_8"], tile["staged_epilogue"], tile["cta_group"]]}), flush=True)
     del q, k, v, o
