@@ -305,7 +305,10 @@ int launch_variant(int sw, int emu, int stg, const CUtensorMap& tq, const CUtens
 }
 
 // CTA-pair kernel (d = 128, 8 softmax warps): clusters of two CTAs, 512-row work items, one claim per pair.
-constexpr int kPairStages = 6;      // 16 KiB ring slots: three K halves + three V halves in flight
+#ifndef FA_PAIR_STAGES
+#define FA_PAIR_STAGES 6
+#endif
+constexpr int kPairStages = FA_PAIR_STAGES;      // 16 KiB ring slots: three K halves + three V halves in flight (8 fit and measure the same)
 template <int DT, bool OVEC32, int ST>
 int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMap& tv, const CUtensorMap& to, fa::FwdParams p, cudaStream_t st) {
     constexpr int D = 128;
