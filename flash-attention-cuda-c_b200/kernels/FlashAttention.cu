@@ -198,7 +198,7 @@ const fa_tile_choice_t kTileTable[] = {
     { 64, 1,  8192,  256, 128, 8, 16, 1, 0, 0, 1,  790.0f},   // +0.6 % at 8K, +1.7 % at 16K, +2.2 % at 32K
 };
 constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
-std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_force_cg{0}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
+std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_force_cg{0}, g_pair_heads{1}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
 
 const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
     const fa_tile_choice_t* best = nullptr;
@@ -207,6 +207,18 @@ const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
         if (r.d == d && r.causal == (causal ? 1 : 0) && nk >= r.n_min && (!best || r.n_min >= best->n_min)) best = &r;
     }
     return best;
+}
+
+int device_sm_count() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static std::atomic<int> sms[64];
+    int v = sms[dev & 63].load();
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev & 63].store(v);
+    }
+    return v;
 }
 
 // ---- tcgen05 path ----------------------------------------------------------------------------------
@@ -334,8 +346,12 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMa
         if (getenv("FA_DEBUG_PAIRS")) fprintf(stderr, "fa_b200: device %d holds %d CTA pairs at once\n", dev, n);
         dev_mask.fetch_or(1ull << dev);
     }
-    const int num_q_blocks = (p.Nq + fa::kPairRows - 1) / fa::kPairRows;
-    const long long items = (long long)num_q_blocks * p.Hq * p.B;
+    // pairs by heads when every kv group has an even number of query heads (no causal loss, 256-row items), else by rows
+    const int by_heads = (p.q_heads_per_kv % 2 == 0 && g_pair_heads.load() != 0) ? 1 : 0;
+    const int item_rows = by_heads ? fa::kTilesPerCta * fa::kBlockM : fa::kPairRows;
+    const int item_heads = by_heads ? p.Hq / 2 : p.Hq;
+    const int num_q_blocks = (p.Nq + item_rows - 1) / item_rows;
+    const long long items = (long long)num_q_blocks * item_heads * p.B;
     if (items > 0x3fffffffLL - 4096) return fail(FA_ERR_INVALID_ARGUMENT, "too many work items (%lld)", items);
     int sm_count = 0;
     int* counter = next_counter(st, &sm_count);
@@ -345,8 +361,9 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMa
     if (by_reserve < max_pairs) max_pairs = by_reserve;
     if (max_pairs < 1) max_pairs = 1;
     p.num_q_blocks = num_q_blocks;
+    p.pair_heads = by_heads;
     make_fast_div((unsigned)p.num_q_blocks, &p.div_qblocks_mul, &p.div_qblocks_shr);
-    make_fast_div((unsigned)p.Hq, &p.div_hq_mul, &p.div_hq_shr);
+    make_fast_div((unsigned)item_heads, &p.div_hq_mul, &p.div_hq_shr);
     make_fast_div((unsigned)p.q_heads_per_kv, &p.div_group_mul, &p.div_group_shr);
     p.sched_counter = counter;
     p.n_full_items = p.total_items = (int)items;
@@ -444,6 +461,7 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     p.scale = sc; p.scale_log2 = sc * 1.4426950408889634f;
     p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
     p.prof = g_prof;
+    p.pair_heads = 0;
 
     // kernel variant: from the measured tile table, unless an A/B tool forces one
     const fa_tile_choice_t* tc = choose_tile(d, causal, Nk);
@@ -460,6 +478,20 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     const bool v32 = !carry && reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0;
     const bool bf = dtype == FA_DTYPE_BF16;
     int cg = tc ? tc->cta_group : 1;
+    if (!g_force_cg.load() && d == 128 && sw == 8) {
+        // GQA with an even number of query heads per kv group: the pair kernel cuts its pairs by HEADS (same rows, same diagonal,
+        // 256-row items), so the causal loss that keeps the table's causal rows below 8K on 1-CTA kernels does not exist:
+        // +4.2 .. +4.8 % at causal 2K .. 32K, +6 % at 1K (Hq/Hkv = 32/8; profiles/r2_sustained_gqa_pairs_by_heads.log)
+        const bool by_heads = (Hq / Hkv) % 2 == 0 && g_pair_heads.load() != 0;
+        if (by_heads) cg = 2;
+        // Small launches stay on 1-CTA kernels: below four waves of pair items the pairing buys nothing (such launches are
+        // not power-limited) and the 1-CTA kernels' half-item tail schedule fills the SMs better (96 pair items: -6 %).
+        if (cg == 2) {
+            const long long rows = by_heads ? fa::kTilesPerCta * fa::kBlockM : fa::kPairRows;
+            const long long items = (long long)((Nq + rows - 1) / rows) * (by_heads ? Hq / 2 : Hq) * B;
+            if (items < 4LL * (device_sm_count() / 2)) cg = 1;
+        }
+    }
     if (g_force_cg.load()) cg = g_force_cg.load();
     // A reserve of 8 or more SMs means a communication KERNEL runs beside the attention launch (NCCL send/recv in the ring's
     // p2p transport).  Its CTAs land on SMs of different TPCs, a TPC with one SM taken cannot hold a pair, and the pairs that
@@ -710,10 +742,12 @@ int fa_debug_force_variant(int softmax_warps, int emu, int staged) {
     g_force_stg.store(staged);
     return FA_OK;
 }
-// 0 = as the tile table says, 1 = 1-CTA kernels, 2 = the CTA-pair kernel wherever it exists (d = 128, 8 softmax warps)
+// 0 = as the tile table says, 1 = 1-CTA kernels, 2 = the CTA-pair kernel wherever it exists (d = 128, 8 softmax warps);
+// 3 = the pair kernel with pairs cut by ROWS even where they could be cut by heads (GQA): the A/B of the two pairings
 int fa_debug_force_cta_group(int cta_group) {
-    if (cta_group < 0 || cta_group > 2) return FA_ERR_INVALID_ARGUMENT;
-    g_force_cg.store(cta_group);
+    if (cta_group < 0 || cta_group > 3) return FA_ERR_INVALID_ARGUMENT;
+    g_force_cg.store(cta_group == 3 ? 2 : cta_group);
+    g_pair_heads.store(cta_group == 3 ? 0 : 1);
     return FA_OK;
 }
 int fa_debug_plan_counts(long long blocks, int max_ctas, long long* n_full, long long* total) {

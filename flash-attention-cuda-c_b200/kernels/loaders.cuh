@@ -114,6 +114,8 @@ struct FwdParams {
     int n_full_items;        // the first n_full_items query blocks (in queue order) are one 256-row item each; the rest are split in halves
     int split_half;          // 1: a half item runs on BOTH query-tile slots — slot t takes key tiles t, t+2, ... of the same 128 rows and
                              //    the two partial results are merged in the epilogue (8-warp layouts, plain mode); 0: slot 0 alone
+    int pair_heads;          // CTA-pair kernel: 1 = the two CTAs of a pair take two query HEADS of one kv group over the same 256 rows
+                             //    (Hq / Hkv even), 0 = two 128-row halves of each 256-row MMA tile of a 512-row block of one head
     int* sched_counter;      // device int, zero at launch and left zero by the launch: next work item = gridDim.x + atomicAdd(counter, 1)
     unsigned long long* prof; // FA_PHASE_PROFILE builds only: per-phase cycle counters (see scripts/phase_profile.py)
 };
@@ -353,36 +355,45 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTA-pair kernel (d = 128): a work item is a 512-row query block of one (batch, head).  MMA tile t (t = 0, 1) of the pair is
-// the 256 rows [q0 + 256 t, q0 + 256 t + 256): the leader CTA owns the first 128 of them, the peer the last 128, each in its
-// own TMEM lanes.  Tile counts are those of the whole 256-row MMA tile (the leader's half of a causal tile's last key tile is
-// fully masked: its softmax sees -inf and writes P = 0).
+// CTA-pair kernel (d = 128).  Every MMA covers 256 query rows, 128 from each CTA, against ONE K / V tile — the two CTAs must
+// want the same keys at the same time.  Two ways to cut the work:
+//   by rows  (any head layout): a work item is a 512-row query block of one (batch, head); MMA tile t is the rows
+//            [q0 + 256 t, q0 + 256 t + 256), the leader CTA owns the first 128 of them, the peer the last 128.  Tile counts are
+//            those of the whole 256-row tile: on a causal diagonal the leader's half of the tile's last key tile is fully masked
+//            (its softmax sees -inf and writes P = 0) — one step per item more than two 1-CTA items would take.
+//   by heads (Hq / Hkv even): a work item is a 256-row block of TWO query heads of one kv group; the leader takes head 2 hp, the
+//            peer head 2 hp + 1, both the same rows.  Same keys, same diagonal, same mask: nothing is lost on causal problems,
+//            and items are half as long (the scheduling granularity of the 1-CTA kernel).
+// The mailbox carries, per CTA, its own head and first row; `rows` = 512 / 256 tells the stride between the CTA's two tiles.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPairRows = 2 * kTilesPerCta * kBlockM;      // 512
-constexpr int kPairTileRows = 2 * kBlockM;                 // 256
 
 __device__ __forceinline__ WorkItem decode_pair_item(const FwdParams& p, int item) {
     WorkItem w;
-    w.rows = kPairRows;
+    const int by_heads = p.pair_heads;
+    w.rows = by_heads ? kTilesPerCta * kBlockM : kPairRows;
+    const int tile_rows = w.rows / kTilesPerCta;        // rows of one MMA tile that decide its key range: 128 (per CTA) / 256 (both CTAs)
     w.split = 0;
     const int bh = fast_div(item, p.div_qblocks_mul, p.div_qblocks_shr);
     const int r = item - bh * p.num_q_blocks;
     const int qb = p.causal ? (p.num_q_blocks - 1 - r) : r;
+    // by heads, (batch, head PAIR) indexes the items: the host made div_hq for Hq / 2
+    const int heads = by_heads ? (p.Hq >> 1) : p.Hq;
     w.b = fast_div(bh, p.div_hq_mul, p.div_hq_shr);
-    w.h = bh - w.b * p.Hq;
+    w.h = (bh - w.b * heads) << by_heads;               // the leader's head
     w.h_kv = fast_div(w.h, p.div_group_mul, p.div_group_shr);
-    w.q0 = qb * kPairRows;
+    w.q0 = qb * w.rows;
     const int n_all = (p.Nk + kBlockN - 1) / kBlockN;
     w.n_kv = 0;
 #pragma unroll
     for (int t = 0; t < kTilesPerCta; ++t) {
         int n = n_all;
         if (p.causal) {
-            const int last_col = w.q0 + (t + 1) * kPairTileRows - 1 + p.causal_off;
+            const int last_col = w.q0 + (t + 1) * tile_rows - 1 + p.causal_off;
             const int n_c = last_col < 0 ? 0 : last_col / kBlockN + 1;
             n = n_c < n ? n_c : n;
         }
-        if (w.q0 + t * kPairTileRows >= p.Nq) n = 0;
+        if (w.q0 + t * tile_rows >= p.Nq) n = 0;
         if (t == 0) w.n_tile0 = n; else w.n_tile1 = n;
         w.n_kv = n > w.n_kv ? n : w.n_kv;
     }
@@ -419,8 +430,9 @@ __device__ __forceinline__ void tmaPairLoaderThread(const CUtensorMap* tmQ, cons
 #pragma unroll
             for (uint32_t c = 0; c < 2; ++c) {
                 const uint32_t a = mapa_shared(smem_base + L::kSchedItemOff + L::kSchedSlotBytes * slot, c);
-                st_shared_cluster_v4(a, pub, w.b, w.h, w.h_kv);
-                st_shared_cluster_v4(a + 16, w.q0 + int(c) * kBlockM, w.rows, 0, w.n_kv);
+                // the peer's own head (pairs by heads) or own first row (pairs by rows)
+                st_shared_cluster_v4(a, pub, w.b, w.h + (p.pair_heads ? int(c) : 0), w.h_kv);
+                st_shared_cluster_v4(a + 16, w.q0 + (p.pair_heads ? 0 : int(c) * kBlockM), w.rows, 0, w.n_kv);
                 st_shared_cluster_v4(a + 32, w.n_steps, w.n_tile0, w.n_tile1, 0);
                 mbar_arrive_cluster_release(mapa_shared(bar0 + 8 * (L::kBarSchedFull + slot), c));
             }
@@ -443,7 +455,7 @@ __device__ __forceinline__ void tmaPairLoaderThread(const CUtensorMap* tmQ, cons
 #pragma unroll
                 for (int hf = 0; hf < D / kHalfCols; ++hf)
                     tma_load_4d_pair(tmQ, smem_base + L::kQOff + t * L::kQTileBytes + hf * kHalfBytes, q_full_l,
-                                     hf * kHalfCols, w.q0 + t * kPairTileRows, w.h, w.b, kEvictFirst);
+                                     hf * kHalfCols, w.q0 + t * (w.rows >> 1), w.h, w.b, kEvictFirst);
             for (int j = 0; j < w.n_kv; ++j) {
                 {   // this CTA's 64 keys of K_j, both 64-column halves
                     const int s = it % STAGES;

@@ -8,7 +8,13 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "flash-attention-cuda-c_b200")]
 import torch, fa_b200
 SHAPES = [(8, 32, 32, 8192, 128, True, "bf16"), (8, 32, 32, 8192, 128, False, "bf16"), (32, 32, 32, 2048, 128, True, "bf16"),
           (8, 32, 32, 8192, 64, True, "bf16"), (64, 32, 32, 1024, 128, True, "bf16"), (4, 12, 12, 1024, 64, False, "fp16"),
-          (16, 32, 32, 4096, 128, True, "bf16"), (4, 32, 32, 16384, 128, True, "bf16"), (16, 32, 32, 4096, 128, False, "bf16"), (128, 32, 32, 512, 128, True, "bf16")]
+          (16, 32, 32, 4096, 128, True, "bf16"), (4, 32, 32, 16384, 128, True, "bf16"), (16, 32, 32, 4096, 128, False, "bf16"), (128, 32, 32, 512, 128, True, "bf16"),
+          # GQA 32/8 (10..14): the pair kernel can cut its pairs by heads there
+          (64, 32, 8, 1024, 128, True, "bf16"), (32, 32, 8, 2048, 128, True, "bf16"), (16, 32, 8, 4096, 128, True, "bf16"), (8, 32, 8, 8192, 128, True, "bf16"),
+          (1, 64, 8, 32768, 128, True, "bf16"),
+          # small launches (15..19): 96 / 128 / 256 pair items by rows; 128 / 64 by heads
+          (4, 12, 12, 1024, 128, False, "bf16"), (2, 16, 16, 2048, 128, False, "bf16"), (4, 16, 16, 2048, 128, False, "bf16"),
+          (2, 16, 4, 2048, 128, True, "bf16"), (1, 16, 4, 2048, 128, False, "bf16")]
 names = sys.argv[1:]
 sel = [int(x) for x in os.environ.get("FA_AB_SHAPES", "0").split(",")]
 rounds = int(os.environ.get("FA_SUS_ROUNDS", "6")); n = int(os.environ.get("FA_SUS_N", "120")); warm = int(os.environ.get("FA_SUS_WARM", "40"))

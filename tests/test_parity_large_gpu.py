@@ -140,14 +140,14 @@ def test_many_work_items_carry_mode(d):
 
 
 # ---- the CTA-pair kernel (clusters of 2, tcgen05 cta_group::2) and its 1-CTA counterpart, each forced --------------------
-@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("cta_group", [1, 2, 3])      # 1-CTA kernel; pairs cut by heads (4 query heads per kv group); pairs cut by rows
 @pytest.mark.parametrize("staged", [0, 1])
 @pytest.mark.parametrize("causal,nq,nk", [(False, 1000, 1000), (True, 1000, 1000), (True, 700, 1300), (False, 513, 384), (True, 2100, 2100)])
 def test_cta_pair_and_single_kernels_forced(cta_group, staged, causal, nq, nk):
-    # The tile table picks the pair kernel for d = 128 non-causal and for causal Nk >= 8K; here both kernels run every shape:
-    # 512-row pair items with a ragged last item (rows past Nq in the peer CTA only: nq = 513), fully masked leader half
-    # tiles on every causal diagonal, Nq != Nk, GQA, more items than pairs (6 x 12 x 3..5 items on 74 pairs), LSE.
-    B, Hq, Hkv, d = 6, 12, 4, 128
+    # The launcher picks the pair kernel for large d = 128 launches (MHA: non-causal, causal Nk >= 8K; GQA: always); here every
+    # kernel runs every shape: 512-row pair items with a ragged last item (rows past Nq in the peer CTA only: nq = 513), fully
+    # masked leader half tiles on every causal diagonal, two heads of a kv group in one MMA, Nq != Nk, more items than pairs, LSE.
+    B, Hq, Hkv, d = 6, 12, 3, 128
     dtype = torch.float16 if (nq + staged) % 2 else torch.bfloat16
     q, k, v = _rand((B, Hq, nq, d), dtype, 31), _rand((B, Hkv, nk, d), dtype, 32), _rand((B, Hkv, nk, d), dtype, 33)
     try:
@@ -175,7 +175,7 @@ def test_cta_pair_kernel_bit_identical_to_single_kernel_on_random_shapes():
     try:
         L.fa_debug_half_items(0)
         for i in range(120):
-            g = rng.choice([1, 1, 2, 4, 8])
+            g = rng.choice([1, 1, 2, 3, 4, 8])      # odd groups: pairs cut by rows; even ones: by heads
             Hkv = rng.choice([1, 2, 3]); Hq = Hkv * g
             B = rng.choice([1, 2, 3])
             Nq = rng.choice([1, 17, 128, 129, 255, 256, 257, 511, 512, 513, 700, 1000, 1024, 1500, 2048, rng.randrange(1, 3000)])
