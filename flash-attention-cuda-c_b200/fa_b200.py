@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-line
 
 FA_DTYPE_F32, FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1, 2
 EXPORTS = ["fa_fwd", "fa_fwd_strided", "fa_fwd_carry", "fa_fwd_carry_window", "fa_mha_fwd_f32", "fa_fwd_host", "fa_merge_partial", "fa_cast_out",
-           "fa_set_sm_reserve", "fa_device_info", "fa_block_q", "fa_block_kv", "fa_tile_table", "fa_choose_tile", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
+           "fa_workspace_bytes", "fa_set_sm_reserve", "fa_device_info", "fa_block_q", "fa_block_kv", "fa_tile_table", "fa_choose_tile", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
 
 _lib = None
 
@@ -78,6 +78,7 @@ def lib() -> ctypes.CDLL:
             "fa_device_info": [ip, vp],
             "fa_tile_table": [ctypes.POINTER(ctypes.POINTER(TileChoice))],
             "fa_choose_tile": [ip] * 5 + [ctypes.POINTER(TileChoice)],
+            "fa_workspace_bytes": [ip] * 7,
             "fa_debug_force_variant": [ip, ip, ip],
             "fa_debug_half_items": [ip],
             "fa_set_sm_reserve": [ip],

@@ -761,6 +761,19 @@ int fa_debug_fast_div(unsigned d, unsigned n) {      // what the kernels compute
     return shr >= 32u ? (int)n : (int)((((unsigned long long)n * mul) >> 32) >> shr);
 }
 int fa_debug_half_items(int on) { g_half_items.store(on ? 1 : 0); g_split_half.store(on > 1 ? 0 : 1); return FA_OK; }   // 0: off, 1: on (split-KV), 2: on, slot 0 alone
+int fa_workspace_bytes(int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype) {
+    g_err[0] = 0;
+    if (B <= 0 || Hq <= 0 || Hkv <= 0 || Nq <= 0 || Nk <= 0 || d <= 0) return fail(FA_ERR_INVALID_ARGUMENT, "non-positive size");
+    if (Hq % Hkv != 0) return fail(FA_ERR_INVALID_ARGUMENT, "Hq=%d is not a multiple of Hkv=%d", Hq, Hkv);
+    if (dtype == FA_DTYPE_F32) {
+        if (d % 16 != 0 || d > 128) return fail(FA_ERR_UNSUPPORTED, "fp32 path needs d %% 16 == 0 and d <= 128 (got %d)", d);
+    } else if (dtype == FA_DTYPE_F16 || dtype == FA_DTYPE_BF16) {
+        if (d != 64 && d != 128) return fail(FA_ERR_UNSUPPORTED, "16-bit path supports d in {64,128} (got %d)", d);
+    } else {
+        return fail(FA_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+    }
+    return 0;      // nothing: no workspace, no padding, no transposed copies
+}
 int fa_num_cta(int q_dim, int q_block_size) {
     if (q_dim <= 0 || q_block_size <= 0) return 0;
     return (q_dim + q_block_size - 1) / q_block_size;

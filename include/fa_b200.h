@@ -115,6 +115,13 @@ int fa_fwd_carry_window(const void* Q, const void* K, const void* V, float* acc_
 /* fa_cast_out: fp32 accumulator -> 16-bit output tensor (n elements, n even). */
 int fa_cast_out(const float* src, void* dst, long long n, int dtype, void* stream);
 
+/* fa_workspace_bytes: device scratch a call of this shape needs FROM THE CALLER — always 0.  The kernels keep their state in
+ * shared memory and TMEM, the TMA descriptors travel as kernel parameters, the 4-byte work-item counters are the library's
+ * own (one per device and stream), and ring steps accumulate into the caller's (acc_o, acc_lse) pair.  Exists so that a host
+ * driver written "ask, allocate, call" (the reference's main.cpp:30-33 was to size its buffers before the launch) needs no
+ * special case.  Returns 0, or a negative FA_ERR_* code for a shape fa_fwd would reject. */
+int fa_workspace_bytes(int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype);
+
 /* ---- host helpers (reference: helpers.hpp:8-36, main.cpp:5-26) ----------------------------------------------*/
 typedef struct {
     int cc_major, cc_minor, sm_count;

@@ -82,6 +82,11 @@ def test_argument_validation_without_gpu(L):
     assert L.fa_fwd(p, p, p, p, None, 1, 1, 1, 0, 16, 64, 2, 0.0, 0, None) == -1      # empty sequence
     assert L.fa_fwd(p, p, p, p, None, 1, 1, 1, 16, 16, 64, 7, 0.0, 0, None) == -1     # unknown dtype
     assert L.fa_merge_partial(None, None, None, None, 0, 0, 2, None) == -1
+    # "ask, allocate, call": the answer is always 0 bytes, and the same shapes fa_fwd rejects are rejected here
+    assert L.fa_workspace_bytes(8, 32, 32, 8192, 8192, 128, fa_b200.FA_DTYPE_BF16) == 0
+    assert L.fa_workspace_bytes(16, 64, 8, 32768, 32768, 128, fa_b200.FA_DTYPE_F16) == 0
+    assert L.fa_workspace_bytes(1, 1, 1, 256, 256, 64, fa_b200.FA_DTYPE_F32) == 0
+    assert L.fa_workspace_bytes(1, 3, 2, 16, 16, 64, 2) == -1 and L.fa_workspace_bytes(1, 1, 1, 16, 16, 96, 2) < 0
     assert L.fa_launch_count() == 0                                                    # nothing was launched
 
 
