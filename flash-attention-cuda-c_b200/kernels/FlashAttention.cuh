@@ -11,6 +11,9 @@
 //                                        EMU: share of the exponentials on the FMA pipe; ST: epilogue staged
 //                                        through shared memory and written with TMA stores; HS: half items run split-KV
 //                                        on both query-tile slots — the build small launches with a short last wave get)
+//   fa::fwdSm100PairKernel<D, STAGES, DT, OVEC32, ST> — the same kernel for clusters of two CTAs (d = 128): tcgen05
+//                                        cta_group::2 MMAs over 256 query rows, each CTA loading and reading half of
+//                                        every K/V tile; pairs cut by rows (512-row items) or by the two heads of a kv group
 //   fa::fwdFp32Kernel<D>                — exact-fp32 CUDA-core kernel for fp32 I/O
 // The compat template is launched by the *caller* with a grid/block/shared-memory size of its own choosing
 // (reference: tests/main.cu:51-61 uses grid 1, (QT+2)*32 threads, (3QT+4R)*D*4 bytes), so it cannot take TMA

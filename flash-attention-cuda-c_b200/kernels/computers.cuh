@@ -8,7 +8,8 @@
 //   S   = Q_t K_j^T   (A = Q tile, B = K tile, both K-major in 128B-swizzled smem)    -> the shared S buffer
 //   O_t += P_t V_j    (A = P_t in TMEM as packed 16-bit, B = V tile MN-major in smem) -> O_t
 // issued by TWO issuer warps (one elected lane per batch of MMAs): at d = 128 one warp issues every Q K^T and the other
-// every P V (mmaTypeIssuerWarp), at d = 64 there is one issuer per query tile (mmaIssuerWarp).  Two softmax
+// every P V (mmaTypeIssuerWarp; mmaPairIssuerWarp issues the same schedule as 256-row cta_group::2 MMAs for a CTA pair,
+// fwdSm100PairKernel), at d = 64 there is one issuer per query tile (mmaIssuerWarp).  Two softmax
 // warpgroups (one per query tile) read S with tcgen05.ld in the 32x32b shape — thread i of warp w owns TMEM
 // lane 32*(w%4)+i, i.e. one whole score row, so row max / row sum need no shuffles — and keep the
 // online-softmax state (running max m, running sum l) in registers:
