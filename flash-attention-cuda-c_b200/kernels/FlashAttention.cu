@@ -755,6 +755,41 @@ int fa_debug_plan_counts(long long blocks, int max_ctas, long long* n_full, long
     plan_counts(blocks, max_ctas, true, n_full, total);
     return FA_OK;
 }
+// The work-item decode of the kernels (loaders.cuh: decode_item / decode_pair_item, the same functions compiled for the host)
+// over a whole launch, for the CPU tests.  mode 0: 1-CTA kernels (256-row items + the half-item tail, split-KV or not), 1: CTA pairs
+// cut by rows, 2: CTA pairs cut by heads.  out[i] = {b, h, h_kv, q0, rows, split, n_kv, n_steps, n_tile0, n_tile1, tile stride,
+// cta rank}; pair modes emit one record per CTA of the pair (what the leader writes into that CTA's mailbox).  Returns the
+// number of records, or a negative error code; nothing touches the GPU.
+int fa_debug_decode_items(int mode, int B, int Hq, int Hkv, int Nq, int Nk, int causal, int max_ctas, int split_half, int* out, int cap) {
+    if (mode < 0 || mode > 2 || B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv || Nq <= 0 || Nk <= 0 || max_ctas < 1 || !out) return FA_ERR_INVALID_ARGUMENT;
+    if (mode == 2 && (Hq / Hkv) % 2) return FA_ERR_INVALID_ARGUMENT;
+    fa::FwdParams p = {};
+    p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk; p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
+    const int item_rows = mode == 1 ? fa::kPairRows : fa::kTilesPerCta * fa::kBlockM;
+    const int item_heads = mode == 2 ? Hq / 2 : Hq;
+    p.num_q_blocks = (Nq + item_rows - 1) / item_rows;
+    p.pair_heads = mode == 2;
+    make_fast_div((unsigned)p.num_q_blocks, &p.div_qblocks_mul, &p.div_qblocks_shr);
+    make_fast_div((unsigned)item_heads, &p.div_hq_mul, &p.div_hq_shr);
+    make_fast_div((unsigned)p.q_heads_per_kv, &p.div_group_mul, &p.div_group_shr);
+    const long long blocks = (long long)p.num_q_blocks * item_heads * B;
+    long long n_full = blocks, total = blocks;
+    if (mode == 0) plan_counts(blocks, max_ctas, true, &n_full, &total);
+    p.n_full_items = (int)n_full; p.total_items = (int)total; p.split_half = mode == 0 ? (split_half ? 1 : 0) : 0;
+    int n = 0;
+    for (int item = 0; item < p.total_items; ++item) {
+        const fa::WorkItem w = mode == 0 ? fa::decode_item(p, item) : fa::decode_pair_item(p, item);
+        for (int c = 0; c < (mode == 0 ? 1 : 2); ++c, ++n) {
+            if (n >= cap) return FA_ERR_INVALID_ARGUMENT;
+            int* r = out + 12 * n;
+            r[0] = w.b; r[1] = w.h + (mode == 2 ? c : 0); r[2] = w.h_kv; r[3] = w.q0 + (mode == 1 ? c * fa::kBlockM : 0); r[4] = w.rows; r[5] = w.split;
+            r[6] = w.n_kv; r[7] = w.n_steps; r[8] = w.n_tile0; r[9] = w.n_tile1;
+            r[10] = mode == 0 ? fa::kBlockM : (w.rows >> 1);      // rows between the CTA's two query tiles
+            r[11] = c;
+        }
+    }
+    return n;
+}
 int fa_debug_fast_div(unsigned d, unsigned n) {      // what the kernels compute for n / d (host replica of loaders.cuh: fast_div)
     unsigned mul = 0, shr = 0;
     make_fast_div(d, &mul, &shr);

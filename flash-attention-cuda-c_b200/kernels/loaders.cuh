@@ -166,8 +166,13 @@ struct SmemLayout {
 };
 
 // n / d for 0 <= n < 2^31 with the (mul, shr) pair the host made for d (FlashAttention.cu: make_fast_div): exact
-__device__ __forceinline__ int fast_div(int n, unsigned mul, unsigned shr) {
+// (host-callable too: tests/test_abi.py replays the item decode on the CPU through fa_debug_decode_items)
+__host__ __device__ __forceinline__ int fast_div(int n, unsigned mul, unsigned shr) {
+#ifdef __CUDA_ARCH__
     return shr >= 32u ? n : int(__umulhi(unsigned(n), mul) >> shr);      // shr = 32 marks d == 1
+#else
+    return shr >= 32u ? n : int(unsigned(((unsigned long long)unsigned(n) * mul) >> 32) >> shr);
+#endif
 }
 
 // One work item: a 256-row query block of one (batch, head) — or, for the tail of a small launch, one 128-row half of
@@ -181,15 +186,15 @@ struct WorkItem {
     int n_kv;      // number of 128-row key/value tiles the item loads (that of its busiest query tile)
     int n_steps;   // steps of the item on the shared score buffer: n_kv, or ceil(n_kv / 2) in split-KV mode
     int n_tile0, n_tile1;   // steps each query-tile slot takes part in (causal: the early tile stops one sooner; split: ceil / floor of n_kv / 2)
-    __device__ __forceinline__ int n_tile(int t) const { return t == 0 ? n_tile0 : n_tile1; }
+    __host__ __device__ __forceinline__ int n_tile(int t) const { return t == 0 ? n_tile0 : n_tile1; }
     // key tile slot t multiplies with at its step s, and the first row of slot t's query tile
-    __device__ __forceinline__ int kv_tile(int t, int s) const { return split ? 2 * s + t : s; }
-    __device__ __forceinline__ int tile_row0(int t) const { return split ? q0 : q0 + t * kBlockM; }
+    __host__ __device__ __forceinline__ int kv_tile(int t, int s) const { return split ? 2 * s + t : s; }
+    __host__ __device__ __forceinline__ int tile_row0(int t) const { return split ? q0 : q0 + t * kBlockM; }
 };
 
 // Items are numbered (batch, head)-major so that CTAs running at the same time share K/V through L2; inside a head
 // the heavy (late) causal query blocks come first, which makes the dynamic scheduler an LPT queue.
-__device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
+__host__ __device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int item) {
     WorkItem w;
     int blk = item, half = 0;
     w.rows = kTilesPerCta * kBlockM;
@@ -368,7 +373,7 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
 // ------------------------------------------------------------------------------------------------
 constexpr int kPairRows = 2 * kTilesPerCta * kBlockM;      // 512
 
-__device__ __forceinline__ WorkItem decode_pair_item(const FwdParams& p, int item) {
+__host__ __device__ __forceinline__ WorkItem decode_pair_item(const FwdParams& p, int item) {
     WorkItem w;
     const int by_heads = p.pair_heads;
     w.rows = by_heads ? kTilesPerCta * kBlockM : kPairRows;
