@@ -106,6 +106,9 @@ void run_shard(const Opt& o, Shard& s) {
         }
     };
     pack(hq, bq); pack(hk, bk); pack(hv, bv);
+    // ask, allocate, call: the library needs no scratch of its own (fa_workspace_bytes is 0 for every supported shape and
+    // negative for one fa_fwd would reject), so the four tensors are everything the driver allocates (reference: tests/main.cu:39-43)
+    if (fa_workspace_bytes(int(s.units), g, 1, o.N, o.N, o.d, o.dtype) != 0) return fail("fa_workspace_bytes");
     void *dq, *dk, *dv, *dO;
     if (cudaMalloc(&dq, s.units * q_unit * es) || cudaMalloc(&dk, s.units * kv_unit * es) || cudaMalloc(&dv, s.units * kv_unit * es) ||
         cudaMalloc(&dO, s.units * q_unit * es)) return fail("cudaMalloc");
