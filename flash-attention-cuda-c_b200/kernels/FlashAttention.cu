@@ -317,6 +317,7 @@ int launch_variant(int sw, int emu, int stg, const CUtensorMap& tq, const CUtens
 }
 
 // CTA-pair kernel (d = 128, 8 softmax warps): clusters of two CTAs, 512-row work items, one claim per pair.
+constexpr int kPairUnavailable = 1;      // launch_pair's answer on a device that cannot hold a single cluster of two CTAs
 #ifndef FA_PAIR_STAGES
 #define FA_PAIR_STAGES 6
 #endif
@@ -341,7 +342,7 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMa
         cfg.dynamicSmemBytes = kSmem;
         int n = 0;
         e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-        if (e != cudaSuccess || n < 1) return fail(FA_ERR_CUDA, "cudaOccupancyMaxActiveClusters(pair kernel) -> %s (%d)", cudaGetErrorString(e), n);
+        if (e != cudaSuccess) { cudaGetLastError(); n = 0; }      // e.g. a partition of the GPU on which no TPC has both SMs: no pairs here
         max_pairs_dev[dev & 63].store(n);
         if (getenv("FA_DEBUG_PAIRS")) fprintf(stderr, "fa_b200: device %d holds %d CTA pairs at once\n", dev, n);
         dev_mask.fetch_or(1ull << dev);
@@ -357,6 +358,7 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMa
     int* counter = next_counter(st, &sm_count);
     if (!counter) return fail(FA_ERR_CUDA, "work-item counter allocation failed");
     int max_pairs = max_pairs_dev[dev & 63].load();
+    if (max_pairs < 1) return kPairUnavailable;      // the caller launches the 1-CTA kernel of the same tile-table row instead
     const int by_reserve = (sm_count - g_sm_reserve.load()) / 2;      // fa_set_sm_reserve: SMs left free (small reserves only, see fwd_impl)
     if (by_reserve < max_pairs) max_pairs = by_reserve;
     if (max_pairs < 1) max_pairs = 1;
@@ -502,12 +504,15 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
         // CTA pairs: each CTA loads 64 of a K tile's 128 keys (its own tensor map: 64-row boxes) and 64 of a V tile's columns
         CUtensorMap tk64;
         if (int rc = make_tile_map(&tk64, K, dtype, B, Hkv, Nk, d, s[3], s[4], s[5], 64)) return rc;
+        int rc;
         if (stg) {
-            if (v32) return bf ? launch_pair<fa::kBF16, true, 1>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, true, 1>(tq, tk64, tv, to, p, st);
-            return bf ? launch_pair<fa::kBF16, false, 1>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, false, 1>(tq, tk64, tv, to, p, st);
+            if (v32) rc = bf ? launch_pair<fa::kBF16, true, 1>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, true, 1>(tq, tk64, tv, to, p, st);
+            else rc = bf ? launch_pair<fa::kBF16, false, 1>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, false, 1>(tq, tk64, tv, to, p, st);
+        } else {
+            if (v32) rc = bf ? launch_pair<fa::kBF16, true, 0>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, true, 0>(tq, tk64, tv, to, p, st);
+            else rc = bf ? launch_pair<fa::kBF16, false, 0>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, false, 0>(tq, tk64, tv, to, p, st);
         }
-        if (v32) return bf ? launch_pair<fa::kBF16, true, 0>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, true, 0>(tq, tk64, tv, to, p, st);
-        return bf ? launch_pair<fa::kBF16, false, 0>(tq, tk64, tv, to, p, st) : launch_pair<fa::kF16, false, 0>(tq, tk64, tv, to, p, st);
+        if (rc != kPairUnavailable) return rc;
     }
     if (d == 128) {
         if (v32) return bf ? launch_variant<128, fa::kBF16, true>(sw, emu, stg, tq, tk, tv, to, p, st) : launch_variant<128, fa::kF16, true>(sw, emu, stg, tq, tk, tv, to, p, st);
