@@ -486,12 +486,18 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
         // +4.2 .. +4.8 % at causal 2K .. 32K, +6 % at 1K (Hq/Hkv = 32/8; profiles/r2_sustained_gqa_pairs_by_heads.log)
         const bool by_heads = (Hq / Hkv) % 2 == 0 && g_pair_heads.load() != 0;
         if (by_heads) cg = 2;
-        // Small launches stay on 1-CTA kernels: below four waves of pair items the pairing buys nothing (such launches are
-        // not power-limited) and the 1-CTA kernels' half-item tail schedule fills the SMs better (96 pair items: -6 %).
+        // Small launches: whenever the 1-CTA plan would smooth its tail with half items (at most three waves of 256-row blocks and
+        // a last wave that leaves more than half of the SMs idle, plan_counts), the 1-CTA kernel keeps the launch — the pair
+        // kernel has no half items, and such launches gain nothing from pairing (96 pair items: -6 %, 256: -2 %;
+        // profiles/r2_sustained_small_launch_pairs.log).  Everything else that the table or the head rule gives to pairs runs
+        // on pairs (128 pair items without a half-item tail: +-0).
         if (cg == 2) {
-            const long long rows = by_heads ? fa::kTilesPerCta * fa::kBlockM : fa::kPairRows;
-            const long long items = (long long)((Nq + rows - 1) / rows) * (by_heads ? Hq / 2 : Hq) * B;
-            if (items < 4LL * (device_sm_count() / 2)) cg = 1;
+            const long long blocks = (long long)((Nq + fa::kTilesPerCta * fa::kBlockM - 1) / (fa::kTilesPerCta * fa::kBlockM)) * Hq * B;
+            int ctas = device_sm_count() - g_sm_reserve.load();
+            if (ctas < 1) ctas = 1;
+            long long n_full = 0, total = 0;
+            plan_counts(blocks, ctas, g_half_items.load() != 0, &n_full, &total);
+            if (n_full < blocks) cg = 1;
         }
     }
     if (g_force_cg.load()) cg = g_force_cg.load();
