@@ -198,7 +198,7 @@ const fa_tile_choice_t kTileTable[] = {
     { 64, 1,  8192,  256, 128, 8, 16, 1, 0, 0, 1,  790.0f},   // +0.6 % at 8K, +1.7 % at 16K, +2.2 % at 32K
 };
 constexpr int kTileRows = (int)(sizeof(kTileTable) / sizeof(kTileTable[0]));
-std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_force_cg{0}, g_pair_heads{1}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
+std::atomic<int> g_force_sw{0}, g_force_emu{0}, g_force_stg{0}, g_force_cg{0}, g_pair_heads{4}, g_half_items{1}, g_split_half{1};   // fa_debug_force_variant / fa_debug_half_items (A/B tooling)
 
 const fa_tile_choice_t* choose_tile(int d, int causal, int nk) {
     const fa_tile_choice_t* best = nullptr;
@@ -316,6 +316,14 @@ int launch_variant(int sw, int emu, int stg, const CUtensorMap& tq, const CUtens
               : launch_sm100<D, kStages, DT, OVEC32, 8, 0, 0, 0>(tq, tk, tv, to, p, plan, st);
 }
 
+// query heads per pair item: 4 / 2 / 1 (= pairs cut by rows), capped by fa_debug_force_cta_group's A/B settings
+int pair_heads_for(int q_heads_per_kv) {
+    const int cap = g_pair_heads.load();
+    if (q_heads_per_kv % 4 == 0 && cap >= 4) return 4;
+    if (q_heads_per_kv % 2 == 0 && cap >= 2) return 2;
+    return 1;
+}
+
 // CTA-pair kernel (d = 128, 8 softmax warps): clusters of two CTAs, 512-row work items, one claim per pair.
 constexpr int kPairUnavailable = 1;      // launch_pair's answer on a device that cannot hold a single cluster of two CTAs
 #ifndef FA_PAIR_STAGES
@@ -347,10 +355,11 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMa
         if (getenv("FA_DEBUG_PAIRS")) fprintf(stderr, "fa_b200: device %d holds %d CTA pairs at once\n", dev, n);
         dev_mask.fetch_or(1ull << dev);
     }
-    // pairs by heads when every kv group has an even number of query heads (no causal loss, 256-row items), else by rows
-    const int by_heads = (p.q_heads_per_kv % 2 == 0 && g_pair_heads.load() != 0) ? 1 : 0;
-    const int item_rows = by_heads ? fa::kTilesPerCta * fa::kBlockM : fa::kPairRows;
-    const int item_heads = by_heads ? p.Hq / 2 : p.Hq;
+    // pairs cut by four heads of a kv group where the group size allows it (no causal loss and no "later row block alone" step),
+    // by two heads where it is even (no causal loss), else by rows: loaders.cuh, decode_pair_item
+    const int hpi = pair_heads_for(p.q_heads_per_kv);
+    const int item_rows = fa::kPairRows / hpi;
+    const int item_heads = p.Hq / hpi;
     const int num_q_blocks = (p.Nq + item_rows - 1) / item_rows;
     const long long items = (long long)num_q_blocks * item_heads * p.B;
     if (items > 0x3fffffffLL - 4096) return fail(FA_ERR_INVALID_ARGUMENT, "too many work items (%lld)", items);
@@ -363,7 +372,7 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMa
     if (by_reserve < max_pairs) max_pairs = by_reserve;
     if (max_pairs < 1) max_pairs = 1;
     p.num_q_blocks = num_q_blocks;
-    p.pair_heads = by_heads;
+    p.pair_heads = hpi;
     make_fast_div((unsigned)p.num_q_blocks, &p.div_qblocks_mul, &p.div_qblocks_shr);
     make_fast_div((unsigned)item_heads, &p.div_hq_mul, &p.div_hq_shr);
     make_fast_div((unsigned)p.q_heads_per_kv, &p.div_group_mul, &p.div_group_shr);
@@ -484,8 +493,7 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
         // GQA with an even number of query heads per kv group: the pair kernel cuts its pairs by HEADS (same rows, same diagonal,
         // 256-row items), so the causal loss that keeps the table's causal rows below 8K on 1-CTA kernels does not exist:
         // +4.2 .. +4.8 % at causal 2K .. 32K, +6 % at 1K (Hq/Hkv = 32/8; profiles/r2_sustained_gqa_pairs_by_heads.log)
-        const bool by_heads = (Hq / Hkv) % 2 == 0 && g_pair_heads.load() != 0;
-        if (by_heads) cg = 2;
+        if (pair_heads_for(Hq / Hkv) > 1) cg = 2;
         // Small launches: whenever the 1-CTA plan would smooth its tail with half items (at most three waves of 256-row blocks and
         // a last wave that leaves more than half of the SMs idle, plan_counts), the 1-CTA kernel keeps the launch — the pair
         // kernel has no half items, and such launches gain nothing from pairing (96 pair items: -6 %, 256: -2 %;
@@ -754,11 +762,12 @@ int fa_debug_force_variant(int softmax_warps, int emu, int staged) {
     return FA_OK;
 }
 // 0 = as the tile table says, 1 = 1-CTA kernels, 2 = the CTA-pair kernel wherever it exists (d = 128, 8 softmax warps);
-// 3 = the pair kernel with pairs cut by ROWS even where they could be cut by heads (GQA): the A/B of the two pairings
+// 3 / 4 = the pair kernel with its pairs cut by ROWS / by at most TWO heads even where more heads could share an item (GQA):
+// the A/B of the pairings
 int fa_debug_force_cta_group(int cta_group) {
-    if (cta_group < 0 || cta_group > 3) return FA_ERR_INVALID_ARGUMENT;
-    g_force_cg.store(cta_group == 3 ? 2 : cta_group);
-    g_pair_heads.store(cta_group == 3 ? 0 : 1);
+    if (cta_group < 0 || cta_group > 4) return FA_ERR_INVALID_ARGUMENT;
+    g_force_cg.store(cta_group >= 3 ? 2 : cta_group);
+    g_pair_heads.store(cta_group == 3 ? 1 : (cta_group == 4 ? 2 : 4));
     return FA_OK;
 }
 int fa_debug_plan_counts(long long blocks, int max_ctas, long long* n_full, long long* total) {
@@ -768,18 +777,19 @@ int fa_debug_plan_counts(long long blocks, int max_ctas, long long* n_full, long
 }
 // The work-item decode of the kernels (loaders.cuh: decode_item / decode_pair_item, the same functions compiled for the host)
 // over a whole launch, for the CPU tests.  mode 0: 1-CTA kernels (256-row items + the half-item tail, split-KV or not), 1: CTA pairs
-// cut by rows, 2: CTA pairs cut by heads.  out[i] = {b, h, h_kv, q0, rows, split, n_kv, n_steps, n_tile0, n_tile1, tile stride,
+// cut by rows, 2: by two heads, 3: by four heads.  out[i] = {b, h, h_kv, q0, rows, split, n_kv, n_steps, n_tile0, n_tile1, tile stride,
 // cta rank}; pair modes emit one record per CTA of the pair (what the leader writes into that CTA's mailbox).  Returns the
 // number of records, or a negative error code; nothing touches the GPU.
 int fa_debug_decode_items(int mode, int B, int Hq, int Hkv, int Nq, int Nk, int causal, int max_ctas, int split_half, int* out, int cap) {
-    if (mode < 0 || mode > 2 || B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv || Nq <= 0 || Nk <= 0 || max_ctas < 1 || !out) return FA_ERR_INVALID_ARGUMENT;
-    if (mode == 2 && (Hq / Hkv) % 2) return FA_ERR_INVALID_ARGUMENT;
+    if (mode < 0 || mode > 3 || B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv || Nq <= 0 || Nk <= 0 || max_ctas < 1 || !out) return FA_ERR_INVALID_ARGUMENT;
+    if ((mode == 2 && (Hq / Hkv) % 2) || (mode == 3 && (Hq / Hkv) % 4)) return FA_ERR_INVALID_ARGUMENT;
+    const int hpi = mode == 3 ? 4 : (mode == 2 ? 2 : 1);
     fa::FwdParams p = {};
     p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk; p.causal = causal ? 1 : 0; p.causal_off = Nk - Nq; p.q_heads_per_kv = Hq / Hkv;
-    const int item_rows = mode == 1 ? fa::kPairRows : fa::kTilesPerCta * fa::kBlockM;
-    const int item_heads = mode == 2 ? Hq / 2 : Hq;
+    const int item_rows = mode == 0 ? fa::kTilesPerCta * fa::kBlockM : fa::kPairRows / hpi;
+    const int item_heads = Hq / hpi;
     p.num_q_blocks = (Nq + item_rows - 1) / item_rows;
-    p.pair_heads = mode == 2;
+    p.pair_heads = hpi;
     make_fast_div((unsigned)p.num_q_blocks, &p.div_qblocks_mul, &p.div_qblocks_shr);
     make_fast_div((unsigned)item_heads, &p.div_hq_mul, &p.div_hq_shr);
     make_fast_div((unsigned)p.q_heads_per_kv, &p.div_group_mul, &p.div_group_shr);
@@ -793,9 +803,9 @@ int fa_debug_decode_items(int mode, int B, int Hq, int Hkv, int Nq, int Nk, int 
         for (int c = 0; c < (mode == 0 ? 1 : 2); ++c, ++n) {
             if (n >= cap) return FA_ERR_INVALID_ARGUMENT;
             int* r = out + 12 * n;
-            r[0] = w.b; r[1] = w.h + (mode == 2 ? c : 0); r[2] = w.h_kv; r[3] = w.q0 + (mode == 1 ? c * fa::kBlockM : 0); r[4] = w.rows; r[5] = w.split;
+            r[0] = w.b; r[1] = w.h + (mode ? c * (hpi >> 1) : 0); r[2] = w.h_kv; r[3] = w.q0 + (mode == 1 ? c * fa::kBlockM : 0); r[4] = w.rows; r[5] = w.split;
             r[6] = w.n_kv; r[7] = w.n_steps; r[8] = w.n_tile0; r[9] = w.n_tile1;
-            r[10] = mode == 0 ? fa::kBlockM : (w.rows >> 1);      // rows between the CTA's two query tiles
+            r[10] = mode == 0 ? fa::kBlockM : (w.hstep ? 0 : (w.rows >> 1));      // rows between the CTA's two query tiles (0: two heads instead)
             r[11] = c;
         }
     }

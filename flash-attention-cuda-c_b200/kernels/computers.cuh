@@ -636,9 +636,10 @@ __device__ __forceinline__ void softmaxWarpgroup(uint32_t smem_base, uint32_t tm
         // (Split-KV half item, HS = 1 kernels: both slots hold rows [q0, q0 + 128), slot t takes key tiles t, t+2, ... and slot 0
         // writes the merged result.  The launcher only plans such items when no step needs a mask — non-causal, Nk a multiple
         // of 128 — so the key loop below is untouched: the 216-register loop has no room for a second key-tile numbering.)
-        // (CTA pair: w.q0 is this CTA's own first row of the item, its tile t starts 256 t rows further when the pair splits a
-        // 512-row block by rows and 128 t rows further when it splits by heads: half of the item's `rows`)
-        const int tile_row0 = CG == 2 ? w.q0 + t * (w.rows >> 1) : ((t * kBlockM < w.rows) ? w.q0 + t * kBlockM : kNoRow);
+        // (CTA pair: w.q0 / w.h are this CTA's own first row / head of the item; its tile t starts rows / 2 further — 256 when the
+        // pair cuts a 512-row block by rows, 128 when it cuts by two heads — or, cut by four heads, is the same rows of head h + t)
+        if constexpr (CG == 2) w.h += t * w.hstep;
+        const int tile_row0 = CG == 2 ? w.q0 + (w.hstep ? 0 : t * (w.rows >> 1)) : ((t * kBlockM < w.rows) ? w.q0 + t * kBlockM : kNoRow);
         const int row = tile_row0 + warp_in_wg * 32 + lane;
 
         float m_run = -INFINITY;   // max in use, in raw (unscaled) score units

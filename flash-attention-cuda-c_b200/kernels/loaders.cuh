@@ -114,8 +114,8 @@ struct FwdParams {
     int n_full_items;        // the first n_full_items query blocks (in queue order) are one 256-row item each; the rest are split in halves
     int split_half;          // 1: a half item runs on BOTH query-tile slots — slot t takes key tiles t, t+2, ... of the same 128 rows and
                              //    the two partial results are merged in the epilogue (8-warp layouts, plain mode); 0: slot 0 alone
-    int pair_heads;          // CTA-pair kernel: 1 = the two CTAs of a pair take two query HEADS of one kv group over the same 256 rows
-                             //    (Hq / Hkv even), 0 = two 128-row halves of each 256-row MMA tile of a 512-row block of one head
+    int pair_heads;          // CTA-pair kernel: query heads per work item — 1: pairs cut by rows (512 rows of one head), 2: by two heads
+                             //    of a kv group (256 rows each), 4: by four heads (128 rows each); see decode_pair_item
     int* sched_counter;      // device int, zero at launch and left zero by the launch: next work item = gridDim.x + atomicAdd(counter, 1)
     unsigned long long* prof; // FA_PHASE_PROFILE builds only: per-phase cycle counters (see scripts/phase_profile.py)
 };
@@ -186,6 +186,7 @@ struct WorkItem {
     int n_kv;      // number of 128-row key/value tiles the item loads (that of its busiest query tile)
     int n_steps;   // steps of the item on the shared score buffer: n_kv, or ceil(n_kv / 2) in split-KV mode
     int n_tile0, n_tile1;   // steps each query-tile slot takes part in (causal: the early tile stops one sooner; split: ceil / floor of n_kv / 2)
+    int hstep;     // CTA-pair kernel, pairs cut by four heads: slot t of a CTA works on head h + t (same rows); 0 everywhere else
     __host__ __device__ __forceinline__ int n_tile(int t) const { return t == 0 ? n_tile0 : n_tile1; }
     // key tile slot t multiplies with at its step s, and the first row of slot t's query tile
     __host__ __device__ __forceinline__ int kv_tile(int t, int s) const { return split ? 2 * s + t : s; }
@@ -199,6 +200,7 @@ __host__ __device__ __forceinline__ WorkItem decode_item(const FwdParams& p, int
     int blk = item, half = 0;
     w.rows = kTilesPerCta * kBlockM;
     w.split = 0;
+    w.hstep = 0;
     if (item >= p.n_full_items) {
         const int r = item - p.n_full_items;
         blk = p.n_full_items + (r >> 1);
@@ -253,6 +255,7 @@ __device__ __forceinline__ int fetch_item(uint32_t smem_base, int k, WorkItem& w
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(item), "=r"(w.b), "=r"(w.h), "=r"(w.h_kv) : "r"(a) : "memory");
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.q0), "=r"(w.rows), "=r"(w.split), "=r"(w.n_kv) : "r"(a + 16) : "memory");
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.n_steps), "=r"(w.n_tile0), "=r"(w.n_tile1), "=r"(pad) : "r"(a + 32) : "memory");
+    w.hstep = CG == 2 ? pad : 0;
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
         if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(bar0 + 8 * (L::kBarSchedEmpty + slot), 0));
@@ -361,31 +364,38 @@ __device__ __forceinline__ void tmaLoaderThread(const CUtensorMap* tmQ, const CU
 
 // ------------------------------------------------------------------------------------------------
 // CTA-pair kernel (d = 128).  Every MMA covers 256 query rows, 128 from each CTA, against ONE K / V tile — the two CTAs must
-// want the same keys at the same time.  Two ways to cut the work:
-//   by rows  (any head layout): a work item is a 512-row query block of one (batch, head); MMA tile t is the rows
-//            [q0 + 256 t, q0 + 256 t + 256), the leader CTA owns the first 128 of them, the peer the last 128.  Tile counts are
-//            those of the whole 256-row tile: on a causal diagonal the leader's half of the tile's last key tile is fully masked
-//            (its softmax sees -inf and writes P = 0) — one step per item more than two 1-CTA items would take.
-//   by heads (Hq / Hkv even): a work item is a 256-row block of TWO query heads of one kv group; the leader takes head 2 hp, the
-//            peer head 2 hp + 1, both the same rows.  Same keys, same diagonal, same mask: nothing is lost on causal problems,
-//            and items are half as long (the scheduling granularity of the 1-CTA kernel).
-// The mailbox carries, per CTA, its own head and first row; `rows` = 512 / 256 tells the stride between the CTA's two tiles.
+// want the same keys at the same time.  Three ways to cut the work (FwdParams::pair_heads = heads per item: 1, 2, 4):
+//   by rows    (any head layout): a work item is a 512-row query block of one (batch, head); MMA tile t is the rows
+//              [q0 + 256 t, q0 + 256 t + 256), the leader CTA owns the first 128 of them, the peer the last 128.  Tile counts are
+//              those of the whole 256-row tile: on a causal diagonal the leader's half of the tile's last key tile is fully
+//              masked (its softmax sees -inf and writes P = 0) — one step per item more than two 1-CTA items would take.
+//   by 2 heads (Hq / Hkv even): a work item is a 256-row block of TWO query heads of one kv group; the leader takes head 2 hp,
+//              the peer head 2 hp + 1, both the same rows; slot t of each CTA is the rows [q0 + 128 t, +128).  Same keys, same
+//              diagonal, same mask in both CTAs: nothing is lost on causal problems, items as fine as the 1-CTA kernel's.
+//   by 4 heads (Hq / Hkv a multiple of 4): a work item is a 128-row block of FOUR query heads of one kv group; the leader's
+//              slots take heads 4 hq and 4 hq + 1, the peer's 4 hq + 2 and 4 hq + 3, all four the same 128 rows.  Now the two
+//              slots of a CTA reach the diagonal together as well: the step in which only the later row block has work (one of
+//              every item's n + 1 steps on a causal problem) is gone.
+// The mailbox carries, per CTA, its own first head and first row; `rows` tells the row stride between the CTA's two tiles
+// (rows / 2, or 0 with `hstep` = 1: then slot t works on head h + t).
 // ------------------------------------------------------------------------------------------------
 constexpr int kPairRows = 2 * kTilesPerCta * kBlockM;      // 512
 
 __host__ __device__ __forceinline__ WorkItem decode_pair_item(const FwdParams& p, int item) {
     WorkItem w;
-    const int by_heads = p.pair_heads;
-    w.rows = by_heads ? kTilesPerCta * kBlockM : kPairRows;
-    const int tile_rows = w.rows / kTilesPerCta;        // rows of one MMA tile that decide its key range: 128 (per CTA) / 256 (both CTAs)
+    const int hpi = p.pair_heads;                       // heads per item: 1, 2 or 4
+    w.rows = hpi == 1 ? kPairRows : (hpi == 2 ? kTilesPerCta * kBlockM : kBlockM);
+    w.hstep = hpi == 4 ? 1 : 0;
+    const int tile_rows = hpi == 1 ? 2 * kBlockM : kBlockM;      // rows of one MMA tile that decide its key range: 256 (both CTAs' halves) / 128
+    const int tile_step = hpi == 4 ? 0 : tile_rows;              // rows between the item's two MMA tiles
     w.split = 0;
     const int bh = fast_div(item, p.div_qblocks_mul, p.div_qblocks_shr);
     const int r = item - bh * p.num_q_blocks;
     const int qb = p.causal ? (p.num_q_blocks - 1 - r) : r;
-    // by heads, (batch, head PAIR) indexes the items: the host made div_hq for Hq / 2
-    const int heads = by_heads ? (p.Hq >> 1) : p.Hq;
+    // (batch, head GROUP of hpi heads) indexes the items: the host made div_hq for Hq / hpi
+    const int groups = p.Hq / hpi;
     w.b = fast_div(bh, p.div_hq_mul, p.div_hq_shr);
-    w.h = (bh - w.b * heads) << by_heads;               // the leader's head
+    w.h = (bh - w.b * groups) * hpi;                    // the leader's (first) head
     w.h_kv = fast_div(w.h, p.div_group_mul, p.div_group_shr);
     w.q0 = qb * w.rows;
     const int n_all = (p.Nk + kBlockN - 1) / kBlockN;
@@ -394,11 +404,11 @@ __host__ __device__ __forceinline__ WorkItem decode_pair_item(const FwdParams& p
     for (int t = 0; t < kTilesPerCta; ++t) {
         int n = n_all;
         if (p.causal) {
-            const int last_col = w.q0 + (t + 1) * tile_rows - 1 + p.causal_off;
+            const int last_col = w.q0 + t * tile_step + tile_rows - 1 + p.causal_off;
             const int n_c = last_col < 0 ? 0 : last_col / kBlockN + 1;
             n = n_c < n ? n_c : n;
         }
-        if (w.q0 + t * tile_rows >= p.Nq) n = 0;
+        if (w.q0 + t * tile_step >= p.Nq) n = 0;
         if (t == 0) w.n_tile0 = n; else w.n_tile1 = n;
         w.n_kv = n > w.n_kv ? n : w.n_kv;
     }
@@ -435,10 +445,10 @@ __device__ __forceinline__ void tmaPairLoaderThread(const CUtensorMap* tmQ, cons
 #pragma unroll
             for (uint32_t c = 0; c < 2; ++c) {
                 const uint32_t a = mapa_shared(smem_base + L::kSchedItemOff + L::kSchedSlotBytes * slot, c);
-                // the peer's own head (pairs by heads) or own first row (pairs by rows)
-                st_shared_cluster_v4(a, pub, w.b, w.h + (p.pair_heads ? int(c) : 0), w.h_kv);
-                st_shared_cluster_v4(a + 16, w.q0 + (p.pair_heads ? 0 : int(c) * kBlockM), w.rows, 0, w.n_kv);
-                st_shared_cluster_v4(a + 32, w.n_steps, w.n_tile0, w.n_tile1, 0);
+                // the peer's own first head (pairs by heads: + 1 or + 2) or own first row (pairs by rows)
+                st_shared_cluster_v4(a, pub, w.b, w.h + int(c) * (p.pair_heads >> 1), w.h_kv);
+                st_shared_cluster_v4(a + 16, w.q0 + (p.pair_heads == 1 ? int(c) * kBlockM : 0), w.rows, 0, w.n_kv);
+                st_shared_cluster_v4(a + 32, w.n_steps, w.n_tile0, w.n_tile1, w.hstep);
                 mbar_arrive_cluster_release(mapa_shared(bar0 + 8 * (L::kBarSchedFull + slot), c));
             }
         } else {
@@ -448,6 +458,7 @@ __device__ __forceinline__ void tmaPairLoaderThread(const CUtensorMap* tmQ, cons
             asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pub), "=r"(w.b), "=r"(w.h), "=r"(w.h_kv) : "r"(a) : "memory");
             asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.q0), "=r"(w.rows), "=r"(w.split), "=r"(w.n_kv) : "r"(a + 16) : "memory");
             asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w.n_steps), "=r"(w.n_tile0), "=r"(w.n_tile1), "=r"(pad) : "r"(a + 32) : "memory");
+            w.hstep = pad;
             mbar_arrive_cluster(lead0 + 8 * (L::kBarSchedEmpty + slot));
         }
         if (pub < 0) break;
@@ -460,7 +471,7 @@ __device__ __forceinline__ void tmaPairLoaderThread(const CUtensorMap* tmQ, cons
 #pragma unroll
                 for (int hf = 0; hf < D / kHalfCols; ++hf)
                     tma_load_4d_pair(tmQ, smem_base + L::kQOff + t * L::kQTileBytes + hf * kHalfBytes, q_full_l,
-                                     hf * kHalfCols, w.q0 + t * (w.rows >> 1), w.h, w.b, kEvictFirst);
+                                     hf * kHalfCols, w.q0 + (w.hstep ? 0 : t * (w.rows >> 1)), w.h + t * w.hstep, w.b, kEvictFirst);
             for (int j = 0; j < w.n_kv; ++j) {
                 {   // this CTA's 64 keys of K_j, both 64-column halves
                     const int s = it % STAGES;

@@ -150,8 +150,8 @@ typedef struct {
 } fa_tile_choice_t;
 int fa_tile_table(const fa_tile_choice_t** rows);                                              /* returns the row count */
 /* The row fa_fwd runs for a LARGE launch with Hq == Hkv.  Two launcher rules sit on top of the table (both measured, DESIGN.md
- * §3.1b): with an even number of query heads per kv group the d = 128 pair kernel is used at every length (its pairs are cut
- * by heads, so nothing is lost on causal diagonals), and a small launch whose tail the cta_group 1 kernel would smooth with
+ * §3.1b): with an even number of query heads per kv group the d = 128 pair kernel is used at every length (its work items are
+ * then two or four heads of one kv group over the same rows, so nothing is lost on causal diagonals), and a small launch whose tail the cta_group 1 kernel would smooth with
  * 128-row half items (at most three waves of 256-row blocks, last wave under half full) stays on the cta_group 1 kernel of
  * the same row. */
 int fa_choose_tile(int d, int dtype, int causal, int nq, int nk, fa_tile_choice_t* out);

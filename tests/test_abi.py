@@ -151,17 +151,17 @@ def test_fast_division_of_the_item_decode(L):
 def test_work_item_decode_covers_every_row_once(L):
     # The kernels' item decode (loaders.cuh: decode_item / decode_pair_item, compiled for the host as well) replayed on the CPU
     # for whole launches: every (batch, head, query row) belongs to exactly one query tile of one item — for the 1-CTA kernels
-    # with their half-item / split-KV tail, for CTA pairs cut by rows and for CTA pairs cut by heads — and every tile is given
+    # with their half-item / split-KV tail, for CTA pairs cut by rows, by two heads and by four heads — and every tile is given
     # exactly the key tiles its rows can see (pairs cut by rows: those of the whole 256-row MMA tile, identical in both CTAs).
     import numpy as np
     ip = ctypes.c_int
     L.fa_debug_decode_items.argtypes = [ip] * 9 + [ctypes.POINTER(ip), ip]
     cases = [(1, 3, 3, 1000, 1000, 1), (2, 4, 2, 700, 1300, 1), (1, 2, 2, 513, 384, 0), (2, 8, 2, 2100, 2100, 1), (1, 4, 1, 300, 2000, 1),
-             (3, 6, 3, 129, 640, 0), (1, 2, 2, 1, 1, 1), (2, 2, 2, 900, 500, 1), (4, 12, 12, 1024, 1024, 0)]
-    for mode in (0, 1, 2):
+             (3, 6, 3, 129, 640, 0), (1, 2, 2, 1, 1, 1), (2, 2, 2, 900, 500, 1), (4, 12, 12, 1024, 1024, 0), (2, 16, 2, 777, 777, 1)]
+    for mode in (0, 1, 2, 3):
         for (B, Hq, Hkv, Nq, Nk, causal) in cases:
             group = Hq // Hkv
-            if mode == 2 and group % 2:
+            if (mode == 2 and group % 2) or (mode == 3 and group % 4):
                 continue
             for split_half in ((0, 1) if mode == 0 else (0,)):
                 cap = 8 * B * Hq * (Nq // 128 + 2)
@@ -178,6 +178,7 @@ def test_work_item_decode_covers_every_row_once(L):
                     return 0 if last_row + off < 0 else min(n_all, (last_row + off) // 128 + 1)
                 for b, h, hkv, q0, rows, split, n_kv, n_steps, nt0, nt1, stride, rank in rec.tolist():
                     assert hkv == h // group and 0 <= b < B and 0 <= h < Hq
+                    hstep = 1 if mode == 3 else 0      # pairs cut by four heads: slot t is head h + t, same rows
                     assert n_kv == max(nt0, nt1) or split
                     if split and q0 >= Nq:             # the second half of a ragged last block: nothing to do
                         assert n_kv == 0 and nt0 == 0 and nt1 == 0
@@ -189,6 +190,8 @@ def test_work_item_decode_covers_every_row_once(L):
                     assert n_steps == n_kv
                     for t, nt in ((0, nt0), (1, nt1)):
                         r0 = q0 + t * stride
+                        ht = h + t * hstep
+                        assert ht // group == hkv
                         if mode == 0 and t * 128 >= rows:      # half item on slot 0 alone: slot 1 has no rows
                             assert nt == 0
                             continue
@@ -197,7 +200,7 @@ def test_work_item_decode_covers_every_row_once(L):
                             # leader half has rows (then it runs in lock-step on zero-filled Q rows and stores nothing)
                             assert nt == 0 or (mode == 1 and rank == 1 and r0 - 128 < Nq)
                             continue
-                        cover[b, h, r0:min(r0 + 128, Nq)] += 1
+                        cover[b, ht, r0:min(r0 + 128, Nq)] += 1
                         if mode == 1:                          # the MMA tile is 256 rows: leader rows r0.., peer rows r0 + 128..
                             first = r0 - 128 * rank
                             assert nt == visible_tiles(first + 255)
@@ -207,5 +210,7 @@ def test_work_item_decode_covers_every_row_once(L):
                 if mode:                                   # the two CTAs of a pair walk the same steps
                     a, c = rec[0::2], rec[1::2]
                     assert (a[:, [0, 2, 4, 6, 7, 8, 9]] == c[:, [0, 2, 4, 6, 7, 8, 9]]).all()
-                    assert (c[:, 1] - a[:, 1] == (1 if mode == 2 else 0)).all() and (c[:, 3] - a[:, 3] == (128 if mode == 1 else 0)).all()
+                    assert (c[:, 1] - a[:, 1] == {1: 0, 2: 1, 3: 2}[mode]).all() and (c[:, 3] - a[:, 3] == (128 if mode == 1 else 0)).all()
+                if mode == 3:                              # both slots of both CTAs reach the diagonal together
+                    assert (rec[:, 8] == rec[:, 9]).all() and (rec[:, 10] == 0).all()
 

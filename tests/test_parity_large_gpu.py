@@ -140,7 +140,7 @@ def test_many_work_items_carry_mode(d):
 
 
 # ---- the CTA-pair kernel (clusters of 2, tcgen05 cta_group::2) and its 1-CTA counterpart, each forced --------------------
-@pytest.mark.parametrize("cta_group", [1, 2, 3])      # 1-CTA kernel; pairs cut by heads (4 query heads per kv group); pairs cut by rows
+@pytest.mark.parametrize("cta_group", [1, 2, 3, 4])   # 1-CTA kernel; pairs cut by four heads (4 query heads per kv group); by rows; by two heads
 @pytest.mark.parametrize("staged", [0, 1])
 @pytest.mark.parametrize("causal,nq,nk", [(False, 1000, 1000), (True, 1000, 1000), (True, 700, 1300), (False, 513, 384), (True, 2100, 2100)])
 def test_cta_pair_and_single_kernels_forced(cta_group, staged, causal, nq, nk):
@@ -186,7 +186,7 @@ def test_cta_pair_kernel_bit_identical_to_single_kernel_on_random_shapes():
             q, k, v = _rand((B, Hq, Nq, 128), dt, 3 * i), _rand((B, Hkv, Nk, 128), dt, 3 * i + 1), _rand((B, Hkv, Nk, 128), dt, 3 * i + 2)
             fa_b200.force_variant(8, 0, stg, 1)
             o1, l1 = fa_b200.attention_forward(q, k, v, causal=causal, return_lse=True)
-            fa_b200.force_variant(8, 0, stg, 2)
+            fa_b200.force_variant(8, 0, stg, rng.choice([2, 2, 3, 4]))      # pairs cut by as many heads as the group allows / by rows / by <= 2 heads
             o2, l2 = fa_b200.attention_forward(q, k, v, causal=causal, return_lse=True)
             torch.cuda.synchronize()
             what = f"shape {i}: B{B} Hq{Hq} Hkv{Hkv} Nq{Nq} Nk{Nk} causal={causal} {dt} staged={stg}"
