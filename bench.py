@@ -463,9 +463,10 @@ def run_ours(args, wl, wl_name):
         k_ms = sum(kernel_ms) / len(kernel_ms)          # this rank's mean per-step time from the per-step event pairs
         kernel_name = "fa::fwdFp32Kernel"
         if dtype != "fp32":      # what the launcher's tile table picks for this workload
-            tc = fa_b200.choose_tile(d, {"bf16": fa_b200.FA_DTYPE_BF16, "fp16": fa_b200.FA_DTYPE_F16}[dtype], causal, N, N)
+            tc = fa_b200.choose_kernel(B, Hq, Hkv, N, N, d, {"bf16": fa_b200.FA_DTYPE_BF16, "fp16": fa_b200.FA_DTYPE_F16}[dtype], causal)
             kernel_name = "fa::fwdSm100PairKernel (CTA pairs, cta_group::2)" if tc["cta_group"] == 2 else "fa::fwdSm100Kernel"
-            kernel_name += f" [softmax warps {tc['softmax_warps']}, staged epilogue {tc['staged_epilogue']}, ring slots {tc['stages']}]"
+            kernel_name += (f" [softmax warps {tc['softmax_warps']}, staged epilogue {tc['staged_epilogue']}, ring slots {tc['stages']}, "
+                            f"{tc['work_items']} work items, {tc['heads_per_item']} head(s) per item]")
         per_gpu = F / (k_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")

@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-line
 
 FA_DTYPE_F32, FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1, 2
 EXPORTS = ["fa_fwd", "fa_fwd_strided", "fa_fwd_carry", "fa_fwd_carry_window", "fa_mha_fwd_f32", "fa_fwd_host", "fa_merge_partial", "fa_cast_out",
-           "fa_workspace_bytes", "fa_set_sm_reserve", "fa_device_info", "fa_block_q", "fa_block_kv", "fa_tile_table", "fa_choose_tile", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
+           "fa_workspace_bytes", "fa_set_sm_reserve", "fa_device_info", "fa_block_q", "fa_block_kv", "fa_tile_table", "fa_choose_tile", "fa_choose_kernel", "fa_num_cta", "fa_last_error", "fa_launch_count", "fa_version"]
 
 _lib = None
 
@@ -42,6 +42,11 @@ class TileChoice(ctypes.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class KernelChoice(ctypes.Structure):
+    """fa_kernel_choice_t: what fa_fwd launches for one problem (table row as it runs + the launcher's GQA / small-launch rules)."""
+    _fields_ = [("tile", TileChoice), ("heads_per_item", ctypes.c_int), ("work_items", ctypes.c_longlong)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -78,6 +83,7 @@ def lib() -> ctypes.CDLL:
             "fa_device_info": [ip, vp],
             "fa_tile_table": [ctypes.POINTER(ctypes.POINTER(TileChoice))],
             "fa_choose_tile": [ip] * 5 + [ctypes.POINTER(TileChoice)],
+            "fa_choose_kernel": [ip] * 8 + [ctypes.POINTER(KernelChoice)],
             "fa_workspace_bytes": [ip] * 7,
             "fa_debug_force_variant": [ip, ip, ip],
             "fa_debug_half_items": [ip],
@@ -226,6 +232,16 @@ def choose_tile(d, dtype_code, causal, nq, nk):
     out = TileChoice()
     _check(lib().fa_choose_tile(d, dtype_code, int(bool(causal)), nq, nk, ctypes.byref(out)), "fa_choose_tile")
     return out.as_dict()
+
+
+def choose_kernel(B, Hq, Hkv, Nq, Nk, d, dtype_code, causal):
+    """Exactly what fa_fwd would launch for this problem (fa_choose_kernel): the tile row as it runs, heads per pair item, items."""
+    out = KernelChoice()
+    _check(lib().fa_choose_kernel(B, Hq, Hkv, Nq, Nk, d, dtype_code, int(bool(causal)), ctypes.byref(out)), "fa_choose_kernel")
+    r = out.tile.as_dict()
+    r["heads_per_item"] = out.heads_per_item
+    r["work_items"] = out.work_items
+    return r
 
 
 def force_variant(softmax_warps=0, emu=0, staged=0, cta_group=0):

@@ -215,7 +215,10 @@ int device_sm_count() {
     static std::atomic<int> sms[64];
     int v = sms[dev & 63].load();
     if (!v) {
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) {
+            cudaGetLastError();
+            return 148;      // no device to ask (fa_choose_kernel on a CPU-only box): a B200's count
+        }
         sms[dev & 63].store(v);
     }
     return v;
@@ -322,6 +325,50 @@ int pair_heads_for(int q_heads_per_kv) {
     if (q_heads_per_kv % 4 == 0 && cap >= 4) return 4;
     if (q_heads_per_kv % 2 == 0 && cap >= 2) return 2;
     return 1;
+}
+
+// What a 16-bit launch runs: the tile-table row for (d, causal, Nk) and, on top of it, the launcher's rules.  Pure host
+// arithmetic (fa_choose_kernel exposes it; tests/test_abi.py checks it on the CPU).
+struct KernelChoice { int sw, emu, stg, cg, heads_per_item; const fa_tile_choice_t* row; };
+KernelChoice choose_kernel(int B, int Hq, int Hkv, int Nq, int Nk, int d, int causal, bool carry) {
+    KernelChoice k;
+    k.row = choose_tile(d, causal, Nk);
+    k.sw = k.row ? k.row->softmax_warps : 8;
+    k.emu = k.row ? k.row->emu_pairs_per_8 : 0;
+    k.stg = k.row ? k.row->staged_epilogue : 0;
+    if (g_force_sw.load()) { k.sw = g_force_sw.load(); k.emu = g_force_emu.load(); k.stg = g_force_stg.load(); }
+    if (carry) k.stg = 0;      // carry mode folds into an fp32 accumulator in place: there is no 16-bit O to stage
+    k.cg = k.row ? k.row->cta_group : 1;
+    const bool forced = g_force_cg.load() != 0;
+    const int hpi = pair_heads_for(Hq / Hkv);
+    if (!forced && d == 128 && k.sw == 8) {
+        // GQA with an even number of query heads per kv group: the pair kernel cuts its pairs by HEADS (same rows, same diagonal),
+        // so the causal loss that keeps the table's causal rows below 8K on 1-CTA kernels does not exist: +4.4 .. +12 % at causal
+        // 1K .. 32K (Hq/Hkv = 32/8; profiles/r2_sustained_gqa_pairs_by_four_heads.log)
+        if (hpi > 1) k.cg = 2;
+        // Small launches: whenever the 1-CTA plan would smooth its tail with half items (at most three waves of 256-row blocks and
+        // a last wave that leaves more than half of the SMs idle, plan_counts), the 1-CTA kernel keeps the launch — the pair
+        // kernel has no half items, and such launches gain nothing from pairing (96 pair items: -6 %, 256: -2 %;
+        // profiles/r2_sustained_small_launch_pairs.log).  Everything else that the table or the head rule gives to pairs runs
+        // on pairs (128 pair items without a half-item tail: +-0).
+        if (k.cg == 2) {
+            const long long blocks = (long long)((Nq + fa::kTilesPerCta * fa::kBlockM - 1) / (fa::kTilesPerCta * fa::kBlockM)) * Hq * B;
+            int ctas = device_sm_count() - g_sm_reserve.load();
+            if (ctas < 1) ctas = 1;
+            long long n_full = 0, total = 0;
+            plan_counts(blocks, ctas, g_half_items.load() != 0, &n_full, &total);
+            if (n_full < blocks) k.cg = 1;
+        }
+    }
+    if (forced) k.cg = g_force_cg.load();
+    // A reserve of 8 or more SMs means a communication KERNEL runs beside the attention launch (NCCL send/recv in the ring's
+    // p2p transport).  Its CTAs land on SMs of different TPCs, a TPC with one SM taken cannot hold a pair, and the pairs that
+    // do not fit queue behind the communication kernel: measured on 2 GPUs, 15.4-16.1 ms per ring pass with pairs against
+    // 13.7 ms with 1-CTA kernels.  So the pair kernel is only used with small reserves (copy-engine transports).
+    if (g_sm_reserve.load() >= 8 && !forced) k.cg = 1;
+    if (!(d == 128 && k.sw == 8)) k.cg = 1;      // the pair kernel exists for d = 128 with 8 softmax warps
+    k.heads_per_item = k.cg == 2 ? hpi : 1;
+    return k;
 }
 
 // CTA-pair kernel (d = 128, 8 softmax warps): clusters of two CTAs, 512-row work items, one claim per pair.
@@ -474,11 +521,9 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     p.prof = g_prof;
     p.pair_heads = 0;
 
-    // kernel variant: from the measured tile table, unless an A/B tool forces one
-    const fa_tile_choice_t* tc = choose_tile(d, causal, Nk);
-    int sw = tc ? tc->softmax_warps : 8, emu = tc ? tc->emu_pairs_per_8 : 0, stg = tc ? tc->staged_epilogue : 0;
-    if (g_force_sw.load()) { sw = g_force_sw.load(); emu = g_force_emu.load(); stg = g_force_stg.load(); }
-    if (carry) stg = 0;      // carry mode folds into an fp32 accumulator in place: there is no 16-bit O to stage
+    // kernel variant: the measured tile table + the launcher's rules (choose_kernel), unless an A/B tool forces one
+    const KernelChoice kc = choose_kernel(B, Hq, Hkv, Nq, Nk, d, causal, carry);
+    const int sw = kc.sw, emu = kc.emu, stg = kc.stg, cg = kc.cg;
 
     // the staged epilogue writes O with TMA stores (16-byte alignment, checked above); otherwise 256-bit epilogue stores need
     // every output row to start 32-byte aligned (carry mode does not write O at all)
@@ -488,32 +533,6 @@ int fwd_impl(const void* Q, const void* K, const void* V, void* O, float* lse, i
     }
     const bool v32 = !carry && reinterpret_cast<uintptr_t>(O) % 32 == 0 && s[9] % 16 == 0 && s[10] % 16 == 0 && s[11] % 16 == 0;
     const bool bf = dtype == FA_DTYPE_BF16;
-    int cg = tc ? tc->cta_group : 1;
-    if (!g_force_cg.load() && d == 128 && sw == 8) {
-        // GQA with an even number of query heads per kv group: the pair kernel cuts its pairs by HEADS (same rows, same diagonal,
-        // 256-row items), so the causal loss that keeps the table's causal rows below 8K on 1-CTA kernels does not exist:
-        // +4.2 .. +4.8 % at causal 2K .. 32K, +6 % at 1K (Hq/Hkv = 32/8; profiles/r2_sustained_gqa_pairs_by_heads.log)
-        if (pair_heads_for(Hq / Hkv) > 1) cg = 2;
-        // Small launches: whenever the 1-CTA plan would smooth its tail with half items (at most three waves of 256-row blocks and
-        // a last wave that leaves more than half of the SMs idle, plan_counts), the 1-CTA kernel keeps the launch — the pair
-        // kernel has no half items, and such launches gain nothing from pairing (96 pair items: -6 %, 256: -2 %;
-        // profiles/r2_sustained_small_launch_pairs.log).  Everything else that the table or the head rule gives to pairs runs
-        // on pairs (128 pair items without a half-item tail: +-0).
-        if (cg == 2) {
-            const long long blocks = (long long)((Nq + fa::kTilesPerCta * fa::kBlockM - 1) / (fa::kTilesPerCta * fa::kBlockM)) * Hq * B;
-            int ctas = device_sm_count() - g_sm_reserve.load();
-            if (ctas < 1) ctas = 1;
-            long long n_full = 0, total = 0;
-            plan_counts(blocks, ctas, g_half_items.load() != 0, &n_full, &total);
-            if (n_full < blocks) cg = 1;
-        }
-    }
-    if (g_force_cg.load()) cg = g_force_cg.load();
-    // A reserve of 8 or more SMs means a communication KERNEL runs beside the attention launch (NCCL send/recv in the ring's
-    // p2p transport).  Its CTAs land on SMs of different TPCs, a TPC with one SM taken cannot hold a pair, and the pairs that
-    // do not fit queue behind the communication kernel: measured on 2 GPUs, 15.4-16.1 ms per ring pass with pairs against
-    // 14.7 ms with 1-CTA kernels.  So the pair kernel is only used with small reserves (copy-engine transports).
-    if (g_sm_reserve.load() >= 8 && !g_force_cg.load()) cg = 1;
     if (cg == 2 && d == 128 && sw == 8) {
         // CTA pairs: each CTA loads 64 of a K tile's 128 keys (its own tensor map: 64-row boxes) and 64 of a V tile's columns
         CUtensorMap tk64;
@@ -750,6 +769,36 @@ int fa_choose_tile(int d, int dtype, int causal, int nq, int nk, fa_tile_choice_
     const fa_tile_choice_t* tc = choose_tile(d, causal, nk);
     if (!tc) return fail(FA_ERR_UNSUPPORTED, "16-bit path supports d in {64,128} (got %d)", d);
     *out = *tc;
+    return FA_OK;
+}
+int fa_choose_kernel(int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype, int causal, fa_kernel_choice_t* out) {
+    g_err[0] = 0;
+    if (!out) return fail(FA_ERR_INVALID_ARGUMENT, "out is null");
+    if (B <= 0 || Hq <= 0 || Hkv <= 0 || Nq <= 0 || Nk <= 0 || Hq % Hkv != 0) return fail(FA_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (int rc = fa_choose_tile(d, dtype, causal, Nq, Nk, &out->tile)) return rc;
+    out->heads_per_item = 1;
+    if (dtype == FA_DTYPE_F32) {
+        out->work_items = (long long)((Nq + fa::kF32Rows - 1) / fa::kF32Rows) * Hq * B;
+        return FA_OK;
+    }
+    const KernelChoice k = choose_kernel(B, Hq, Hkv, Nq, Nk, d, causal, false);
+    out->tile.softmax_warps = k.sw;
+    out->tile.emu_pairs_per_8 = k.emu;
+    out->tile.staged_epilogue = k.stg;
+    out->tile.cta_group = k.cg;
+    out->tile.stages = k.cg == 2 ? kPairStages : (d == 64 ? 8 : (k.stg && k.sw == 8 ? 4 : 5));
+    out->heads_per_item = k.heads_per_item;
+    if (k.cg == 2) {
+        const int rows = fa::kPairRows / k.heads_per_item;
+        out->work_items = (long long)((Nq + rows - 1) / rows) * (Hq / k.heads_per_item) * B;
+    } else {
+        const long long blocks = (long long)((Nq + fa::kTilesPerCta * fa::kBlockM - 1) / (fa::kTilesPerCta * fa::kBlockM)) * Hq * B;
+        int ctas = device_sm_count() - g_sm_reserve.load();
+        if (ctas < 1) ctas = 1;
+        long long n_full = 0, total = 0;
+        plan_counts(blocks, ctas, g_half_items.load() != 0, &n_full, &total);
+        out->work_items = total;
+    }
     return FA_OK;
 }
 // A/B tooling (not in include/fa_b200.h): force a kernel variant for every following launch (0, 0 = back to the table);

@@ -155,6 +155,16 @@ int fa_tile_table(const fa_tile_choice_t** rows);                               
  * 128-row half items (at most three waves of 256-row blocks, last wave under half full) stays on the cta_group 1 kernel of
  * the same row. */
 int fa_choose_tile(int d, int dtype, int causal, int nq, int nk, fa_tile_choice_t* out);
+/* fa_choose_kernel: exactly what fa_fwd launches for this problem on the current device — the table row with the two rules
+ * applied (and the reserve set by fa_set_sm_reserve): `tile` as it runs (cta_group, stages, epilogue), the query heads that
+ * share one work item of the pair kernel (1, 2 or 4; 1 for cta_group 1) and the number of work items in the queue.  Pure host
+ * arithmetic; without a GPU it assumes a B200's 148 SMs. */
+typedef struct {
+    fa_tile_choice_t tile;
+    int heads_per_item;
+    long long work_items;
+} fa_kernel_choice_t;
+int fa_choose_kernel(int B, int Hq, int Hkv, int Nq, int Nk, int d, int dtype, int causal, fa_kernel_choice_t* out);
 /* Replaces getNumCta (reference: helpers.hpp:33-36): CTAs along the query axis; ragged sizes round up, no assert. */
 int fa_num_cta(int q_dim, int q_block_size);
 

@@ -214,3 +214,39 @@ def test_work_item_decode_covers_every_row_once(L):
                 if mode == 3:                              # both slots of both CTAs reach the diagonal together
                     assert (rec[:, 8] == rec[:, 9]).all() and (rec[:, 10] == 0).all()
 
+
+def test_launcher_rules_on_top_of_the_tile_table(L):
+    # fa_choose_kernel = the table row + the launcher's rules, host arithmetic only (148 SMs assumed without a GPU)
+    bf = fa_b200.FA_DTYPE_BF16
+    ck = fa_b200.choose_kernel
+    # BASELINE configs[2] (MHA 8K causal) and its non-causal twin: CTA pairs cut by rows, 512-row items, six half-tile ring slots
+    k = ck(8, 32, 32, 8192, 8192, 128, bf, True)
+    assert (k["cta_group"], k["heads_per_item"], k["stages"], k["staged_epilogue"], k["work_items"]) == (2, 1, 6, 1, 8 * 32 * 16)
+    assert ck(8, 32, 32, 8192, 8192, 128, bf, False)["cta_group"] == 2
+    # MHA causal below 8K: 1-CTA kernel with the staged epilogue (four ring slots)
+    k = ck(16, 32, 32, 4096, 4096, 128, bf, True)
+    assert (k["cta_group"], k["stages"], k["staged_epilogue"], k["work_items"]) == (1, 4, 1, 16 * 32 * 16)
+    # GQA: pairs cut by as many heads of a kv group as the group size allows, at every length
+    k = ck(32, 32, 8, 2048, 2048, 128, bf, True)
+    assert (k["cta_group"], k["heads_per_item"], k["work_items"]) == (2, 4, 32 * 8 * 16)             # 128-row items of four heads
+    k = ck(32, 12, 6, 2048, 2048, 128, bf, True)
+    assert (k["cta_group"], k["heads_per_item"], k["work_items"]) == (2, 2, 32 * 6 * 8)              # 256-row items of two heads
+    assert ck(32, 12, 4, 2048, 2048, 128, bf, True)["cta_group"] == 1                                 # groups of 3: the table's causal row
+    k = ck(16, 64, 8, 32768, 32768, 128, bf, True)                                                    # BASELINE configs[3]
+    assert (k["cta_group"], k["heads_per_item"]) == (2, 4)
+    # small launches whose tail the 1-CTA kernel smooths with half items stay there (192 blocks: 148 full items + 88 halves)
+    k = ck(4, 12, 12, 1024, 1024, 128, bf, False)
+    assert (k["cta_group"], k["work_items"]) == (1, 148 + 2 * 44)
+    assert ck(2, 16, 16, 2048, 2048, 128, bf, False)["cta_group"] == 2                                # 256 blocks, no half-item tail: pairs
+    # d = 64 has no pair kernel; fp32 has one geometry
+    assert ck(8, 32, 8, 8192, 8192, 64, bf, True)["cta_group"] == 1 and ck(8, 32, 8, 8192, 8192, 64, bf, True)["softmax_warps"] == 16
+    assert ck(1, 1, 1, 256, 256, 64, fa_b200.FA_DTYPE_F32, False)["work_items"] == 4
+    # a reserve of 8 SMs (a communication kernel beside the launch) keeps everything on 1-CTA kernels
+    L.fa_set_sm_reserve(8)
+    try:
+        assert ck(8, 32, 32, 8192, 8192, 128, bf, False)["cta_group"] == 1
+    finally:
+        L.fa_set_sm_reserve(0)
+    with pytest.raises(fa_b200.FaError):
+        ck(1, 3, 2, 16, 16, 128, bf, False)
+
