@@ -16,6 +16,8 @@ SHAPES = [  # B, Hq, Hkv, N, d, causal, dtype
     (16, 32, 32, 4096, 128, True, "bf16"), (32, 32, 32, 2048, 128, True, "bf16"), (64, 32, 32, 1024, 128, True, "bf16"),
     (4, 64, 8, 8192, 128, True, "bf16"), (4, 64, 64, 8192, 128, True, "bf16"), (8, 32, 32, 8192, 128, True, "fp16"),
     (8, 32, 32, 8192, 64, True, "bf16"), (8, 32, 32, 8192, 64, False, "bf16"), (4, 12, 12, 1024, 64, False, "fp16"),
+    # GQA 32/8 (Llama-3-8B's real head layout): CTA pairs cut by four heads of a kv group
+    (8, 32, 8, 8192, 128, True, "bf16"), (16, 32, 8, 4096, 128, True, "bf16"), (32, 32, 8, 2048, 128, True, "bf16"), (64, 32, 8, 1024, 128, True, "bf16"),
 ]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 for (B, Hq, Hkv, N, d, causal, dt) in SHAPES:
@@ -44,9 +46,10 @@ for (B, Hq, Hkv, N, d, causal, dt) in SHAPES:
     st = sum(steady) / len(steady)
     F = 4.0 * B * Hq * N * N * d * (0.5 if causal else 1.0)
     by = (2 * B * Hq * N * d + 2 * B * Hkv * N * d) * 2
-    tile = fa_b200.choose_tile(d, fa_b200.FA_DTYPE_BF16, causal, N, N)
+    tile = fa_b200.choose_kernel(B, Hq, Hkv, N, N, d, fa_b200.FA_DTYPE_BF16, causal)
     print(json.dumps({"B": B, "Hq": Hq, "Hkv": Hkv, "N": N, "d": d, "causal": causal, "dtype": dt,
                       "steady_ms": round(st, 4), "steady_tflops": round(F / st / 1e9, 1), "steady_gbs": round(by / st / 1e6, 1),
                       "isolated_ms_median": round(iso, 4), "isolated_tflops": round(F / iso / 1e9, 1),
-                      "variant": [tile["softmax_warps"], tile["emu_pairs_per_8"], tile["staged_epilogue"], tile["cta_group"]]}), flush=True)
+                      "variant": [tile["softmax_warps"], tile["emu_pairs_per_8"], tile["staged_epilogue"], tile["cta_group"]],
+                      "heads_per_item": tile["heads_per_item"], "work_items": tile["work_items"]}), flush=True)
     del q, k, v, o
